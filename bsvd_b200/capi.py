@@ -1,0 +1,81 @@
+"""ctypes binding of the C ABI in include/bsvd_b200.h.
+
+This is the stub a maintainer of the reference would add next to
+Experimental_root/archs/bsvd_arch.py to call the B200 path.  It only
+marshals pointers and sizes; torch is used by callers for device memory and streams, never for
+the arithmetic.  If the shared library is missing the import fails loudly — there is no
+fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbsvd_b200.so")
+
+NUM_LAYERS = 32
+PREC_FP16, PREC_BF16 = 0, 1
+EPI_RELU6, EPI_PIXSHUF, EPI_SKIP_ADD, EPI_SHIFT_STORE, EPI_STRIDE2 = 1, 2, 4, 8, 16
+
+# every symbol include/bsvd_b200.h declares (tests check that the library exports all of them)
+EXPORTS = (
+    "bsvd_create", "bsvd_destroy", "bsvd_last_error", "bsvd_version", "bsvd_set_weights",
+    "bsvd_layer_shape", "bsvd_forward_clip", "bsvd_forward_clip_host", "bsvd_stream_push",
+    "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
+)
+
+
+class BsvdConfig(C.Structure):
+    _fields_ = [("chns", C.c_int * 3), ("mid_ch", C.c_int), ("interm_ch", C.c_int),
+                ("in_ch", C.c_int), ("out_ch", C.c_int), ("act_relu6", C.c_int),
+                ("norm_none", C.c_int), ("precision", C.c_int), ("device", C.c_int)]
+
+
+class BsvdConvDesc(C.Structure):
+    _fields_ = [("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("cin", C.c_int),
+                ("cout", C.c_int), ("flags", C.c_int), ("precision", C.c_int),
+                ("debug_variant", C.c_int)]
+
+
+class BsvdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libbsvd_b200.so (built by __graft_entry__.build()).  Raises if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise BsvdError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The B200 path has no CPU fallback.")
+    lib = C.CDLL(p)
+    vp, ci, cip = C.c_void_p, C.c_int, C.POINTER(C.c_int)
+    lib.bsvd_last_error.restype = C.c_char_p
+    lib.bsvd_version.restype = C.c_char_p
+    lib.bsvd_create.argtypes = [C.POINTER(BsvdConfig), C.POINTER(vp)]
+    lib.bsvd_destroy.argtypes = [vp]
+    lib.bsvd_set_weights.argtypes = [vp, ci, vp, vp, ci, ci]
+    lib.bsvd_layer_shape.argtypes = [vp, ci, cip, cip, cip]
+    lib.bsvd_forward_clip.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.bsvd_forward_clip_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.bsvd_stream_push.argtypes = [vp, vp, vp, vp, ci, ci, ci, cip, vp]
+    lib.bsvd_reset.argtypes = [vp]
+    lib.bsvd_last_launch_count.argtypes = [vp]
+    lib.bsvd_workspace_bytes.argtypes = [vp]
+    lib.bsvd_workspace_bytes.restype = C.c_size_t
+    lib.bsvd_conv_stage.argtypes = [C.POINTER(BsvdConvDesc), vp, vp, vp, vp, vp, vp]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise BsvdError(load_library().bsvd_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,693 @@
+// bsvd_capi.cu — host side of the B200-native BSVD-64 path: weight prepack, TMA tensor maps,
+// the 32-stage clip/stream schedules and the extern "C" boundary declared in include/bsvd_b200.h.
+//
+// Reference being replaced: Experimental_root/archs/bsvd_arch.py (BSVD.forward :490-499,
+// streaming_forward :501-552, DenBlock.forward :374-396, BiBufferConv :53-114, MemSkip :308-322).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bsvd_b200.h"
+#include "conv_tc.cuh"
+
+namespace bsvd {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Stride-1 view: 16-bit NHWC [T][H][W][C]; box = [1][R+2][130][64] (haloed tile of one chunk).
+static int make_map_halo(CUtensorMap* m, const void* base, int T, int H, int W, int C, int R) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)kHaloPx, (cuuint32_t)(R + 2), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(halo) failed: %d", (int)r);
+  return 0;
+}
+// Stride-2 view of the same tensor: [T][H/2][2][W/2][2*C]; box = [1][R][1][128][64] (one tap).
+static int make_map_s2(CUtensorMap* m, const void* base, int T, int H, int W, int C, int R) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)T};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2,
+                           (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)kRunPx, 1, (cuuint32_t)R, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(s2) failed: %d", (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit conversion on the host (round to nearest even, like the device epilogue)
+// ------------------------------------------------------------------------------------------------
+static uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static uint16_t f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x >= 0x7f800000u) return (uint16_t)(sign | (x > 0x7f800000u ? 0x7e00u : 0x7c00u));
+  if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);   // rounds to >= 65520 -> inf
+  if (x < 0x33000001u) return (uint16_t)sign;                // < 2^-25 -> 0
+  int e = (int)(x >> 23) - 127;
+  uint32_t m = (x & 0x7fffffu) | 0x800000u;
+  int shift;
+  uint32_t base;
+  if (e >= -14) { shift = 13; base = (uint32_t)(e + 15) << 10; m &= 0x7fffffu; }
+  else { shift = 13 + (-14 - e); base = 0; }
+  uint32_t q = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) ++q;
+  return (uint16_t)(sign | (base + q));
+}
+static inline uint16_t to16(float f, int bf16) { return bf16 ? f32_to_bf16(f) : f32_to_f16(f); }
+
+// ------------------------------------------------------------------------------------------------
+// one fused conv stage: static description + packed weights + launch
+// ------------------------------------------------------------------------------------------------
+struct StageSpec {
+  int cin = 64, cout = 64;   // reference conv channels
+  int stride = 1;
+  bool relu6 = false, pixshuf = false, skip = false, shift = false;
+  bool resid_in = false, final_out = false, first_im2col = false;
+  // derived
+  int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
+  void derive() {
+    gemm_n = final_out ? 16 : cout;
+    ntile = gemm_n >= 256 ? 256 : gemm_n;
+    rows = (ntile == 256) ? 1 : 2;
+    cin_chunks = first_im2col ? 1 : cin / kChunk;
+    tap_begin = first_im2col ? 4 : 0;
+    tap_end = first_im2col ? 5 : 9;
+  }
+  int ntaps() const { return tap_end - tap_begin; }
+  int n_tiles() const { return gemm_n / ntile; }
+  size_t pack_elems() const { return (size_t)n_tiles() * cin_chunks * ntaps() * ntile * kChunk; }
+};
+
+// GEMM column -> reference output channel (PixelShuffle permutes so that one sub-pixel's channels
+// are contiguous: column q*Cq + c  <-  conv channel c*4 + q, nn.PixelShuffle semantics).
+static inline int col_to_cout(const StageSpec& s, int col) {
+  if (!s.pixshuf) return col;
+  const int cq = s.cout / 4;
+  const int q = col / cq, c = col % cq;
+  return c * 4 + q;
+}
+
+// Repack OIHW fp32 -> [n_tile][chunk][tap][ntile rows][64 k] 16-bit, each 128-byte row stored with
+// its eight 16-byte chunks XOR-swizzled by (row & 7) (SWIZZLE_128B K-major canonical layout).
+static void pack_weights(const StageSpec& s, const float* w, const float* b, int bf16,
+                         std::vector<uint16_t>& pack, std::vector<float>& bias) {
+  pack.assign(s.pack_elems(), 0);
+  bias.assign(s.gemm_n, 0.f);
+  for (int col = 0; col < s.gemm_n; ++col) {
+    const int co = col_to_cout(s, col);
+    if (co < s.cout) bias[col] = b ? b[co] : 0.f;
+  }
+  const int nt_count = s.n_tiles();
+  for (int nt = 0; nt < nt_count; ++nt)
+    for (int c = 0; c < s.cin_chunks; ++c)
+      for (int tap = s.tap_begin; tap < s.tap_end; ++tap) {
+        uint16_t* blk = pack.data() +
+            ((size_t)(nt * s.cin_chunks + c) * s.ntaps() + (tap - s.tap_begin)) * s.ntile * kChunk;
+        for (int n = 0; n < s.ntile; ++n) {
+          const int co = col_to_cout(s, nt * s.ntile + n);
+          if (co >= s.cout) continue;
+          for (int k = 0; k < kChunk; ++k) {
+            float v = 0.f;
+            if (s.first_im2col) {
+              // K index = tap'*cin + ci  (prep kernel writes the 3x3xCin patch per pixel)
+              const int tp = k / s.cin, ci = k % s.cin;
+              if (tp < 9) v = w[((size_t)co * s.cin + ci) * 9 + tp];
+            } else {
+              const int ci = c * kChunk + k;
+              v = w[((size_t)co * s.cin + ci) * 9 + tap];
+            }
+            const int chunk16 = (k >> 3) ^ (n & 7);
+            blk[(size_t)n * kChunk + chunk16 * 8 + (k & 7)] = to16(v, bf16);
+          }
+        }
+      }
+}
+
+struct StageDev {
+  StageSpec spec;
+  void* wpack = nullptr;
+  float* bias = nullptr;
+  bool loaded = false;
+};
+
+struct StageIO {
+  const void* in = nullptr;    // 16-bit NHWC input tensor (full tensor base)
+  int T = 1, H = 0, W = 0;     // input frames / rows / cols
+  void* out = nullptr;
+  void* out_prev = nullptr;
+  void* out_next = nullptr;
+  int ring_mode = 0;
+  int zero_future = 0;
+  const void* skip = nullptr;
+  int skip_C = 0;
+  long long skip_frame_stride = 0;
+  const float* resid_in = nullptr;
+  int resid_C = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <int NTILE, int R>
+static int launch_one(const CUtensorMap& map, const ConvParams& p, int grid, size_t smem,
+                      cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE, R>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_done = true;
+  }
+  conv3x3_tc_kernel<NTILE, R><<<grid, kThreads, smem, st>>>(map, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+struct StageLaunch {
+  CUtensorMap map;
+  ConvParams p;
+  int grid = 0;
+  size_t smem = 0;
+  int ntile = 0, rows = 0;
+};
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// Build the launch record (tensor map + params) of one stage for concrete tensors.
+static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_variant,
+                      StageLaunch* L) {
+  const StageSpec& s = sd.spec;
+  ConvParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = io.H / s.stride, Wo = io.W / s.stride;
+  if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
+  p.T = io.T; p.H = Ho; p.W = Wo;
+  p.cin_chunks = s.cin_chunks;
+  p.n_tiles = s.n_tiles();
+  p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
+  p.xblocks = (Wo + kRunPx - 1) / kRunPx;
+  p.yblocks = (Ho + s.rows - 1) / s.rows;
+  p.total_tiles = p.T * p.yblocks * p.xblocks * p.n_tiles;
+  p.mode = (s.stride == 2) ? 1 : 0;
+  p.cin_total = s.cin;
+  p.w_stage_bytes = (uint32_t)s.ntile * 128u;
+  const size_t budget = 232448 - 2048;   // dynamic smem opt-in limit minus alignment slack/static
+  if (p.mode == 0) {
+    p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
+    p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
+    p.a_stages = 2;
+    const int total_w = s.cin_chunks * s.ntaps();
+    const size_t left = budget - (size_t)p.a_stages * p.a_stage_bytes;
+    if (s.n_tiles() == 1 && (size_t)total_w * p.w_stage_bytes <= left && total_w <= kMaxStages) {
+      p.w_resident = 1;
+      p.w_stages = total_w;
+    } else {
+      p.w_resident = 0;
+      p.w_stages = (int)std::min<size_t>(kMaxStages, left / p.w_stage_bytes);
+      if (p.w_stages < 2) return fail("shared memory budget too small for weight stages");
+    }
+  } else {
+    p.a_tx_bytes = (uint32_t)s.rows * kRunPx * 128u;
+    p.a_stage_bytes = p.a_tx_bytes;
+    const size_t per = (size_t)p.a_stage_bytes + p.w_stage_bytes;
+    int st = (int)std::min<size_t>(kMaxStages, budget / per);
+    if (st < 2) return fail("shared memory budget too small for stride-2 stages");
+    p.a_stages = st; p.w_stages = st; p.w_resident = 0;
+  }
+  p.desc_variant = desc_variant;
+  p.wpack = sd.wpack;
+  p.bias = sd.bias;
+  int flags = 0;
+  if (s.relu6) flags |= EPI_RELU6;
+  if (s.pixshuf) flags |= EPI_PIXSHUF;
+  if (s.skip) flags |= EPI_SKIP;
+  if (s.shift) flags |= EPI_SHIFT;
+  if (s.resid_in) flags |= EPI_RESID_IN;
+  if (s.final_out) flags |= EPI_FINAL;
+  if (bf16) flags |= EPI_BF16;
+  if (io.zero_future) flags |= EPI_ZERO_FUTURE;
+  p.flags = flags;
+  p.out = io.out; p.out_prev = io.out_prev; p.out_next = io.out_next; p.ring_mode = io.ring_mode;
+  if (s.pixshuf) { p.out_C = s.cout / 4; p.out_H = 2 * Ho; p.out_W = 2 * Wo; }
+  else { p.out_C = s.final_out ? 3 : s.cout; p.out_H = Ho; p.out_W = Wo; }
+  p.out_frame_stride = (long long)p.out_H * p.out_W * p.out_C;
+  p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
+  p.resid_in = io.resid_in; p.resid_C = io.resid_C;
+  p.fold = p.out_C / 8;
+  if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");
+  if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
+
+  const int cin_map = s.first_im2col ? kChunk : s.cin;
+  int rc = (p.mode == 0) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
+                         : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
+  if (rc) return rc;
+  L->grid = std::min(p.total_tiles, num_sms());
+  L->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes;
+  L->ntile = s.ntile; L->rows = s.rows;
+  return 0;
+}
+
+static int launch_stage(const StageLaunch& L, cudaStream_t st) {
+  if (L.ntile == 16 && L.rows == 2) return launch_one<16, 2>(L.map, L.p, L.grid, L.smem, st);
+  if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L.map, L.p, L.grid, L.smem, st);
+  if (L.ntile == 128 && L.rows == 2) return launch_one<128, 2>(L.map, L.p, L.grid, L.smem, st);
+  if (L.ntile == 256 && L.rows == 1) return launch_one<256, 1>(L.map, L.p, L.grid, L.smem, st);
+  return fail("no kernel instance for NTILE=%d R=%d", L.ntile, L.rows);
+}
+
+static int upload_stage(StageDev& sd, const float* w, const float* b, int bf16) {
+  std::vector<uint16_t> pack;
+  std::vector<float> bias;
+  pack_weights(sd.spec, w, b, bf16, pack, bias);
+  if (!sd.wpack) CUDA_TRY(cudaMalloc(&sd.wpack, pack.size() * 2));
+  if (!sd.bias) CUDA_TRY(cudaMalloc((void**)&sd.bias, bias.size() * 4));
+  CUDA_TRY(cudaMemcpy(sd.wpack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(sd.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  sd.loaded = true;
+  return 0;
+}
+static void free_stage(StageDev& sd) {
+  if (sd.wpack) cudaFree(sd.wpack);
+  if (sd.bias) cudaFree(sd.bias);
+  sd.wpack = nullptr; sd.bias = nullptr; sd.loaded = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// input staging: fp32 NCHW (+ optional noise map) -> 16-bit NHWC 3x3 patches for inc.convblock.0
+// (the torch.cat of bsvd_arch.py:492-493 and the zero padding of the first conv are folded in).
+// Patch layout per pixel: k = tap*4 + c for tap<9, c<4 ; k in [36,64) = 0.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void prep_patches_kernel(const float* __restrict__ in, const float* __restrict__ nmap,
+                                    uint16_t* __restrict__ out, int T, int in_c, int H, int W) {
+  const long long total = (long long)T * H * W;
+  const long long plane = (long long)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int t = (int)(i / plane);
+    float v[36];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      const bool ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f = 0.f;
+        if (ok) {
+          if (c < in_c) f = __ldg(in + ((long long)t * in_c + c) * plane + (long long)yy * W + xx);
+          else if (nmap) f = __ldg(nmap + (long long)t * plane + (long long)yy * W + xx);
+        }
+        v[tap * 4 + c] = f;
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (j * 8 < 36) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = (j * 8 + k < 36) ? v[j * 8 + k] : 0.f;
+        u.x = pack2<BF16>(f[0], f[1]); u.y = pack2<BF16>(f[2], f[3]);
+        u.z = pack2<BF16>(f[4], f[5]); u.w = pack2<BF16>(f[6], f[7]);
+      }
+      o[j] = u;
+    }
+  }
+}
+
+}  // namespace bsvd
+
+using namespace bsvd;
+
+// ================================================================================================
+// network handle
+// ================================================================================================
+struct bsvd_handle {
+  bsvd_config cfg;
+  int bf16 = 0;
+  StageDev stages[BSVD_NUM_LAYERS];
+  // ---- clip-mode workspace / plan (rebuilt when T,H,W change) ----
+  int pT = 0, pH = 0, pW = 0, p_inc = 0;
+  const float* p_in = nullptr; const float* p_nmap = nullptr; float* p_out = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  uint16_t *bufP = nullptr, *bufA = nullptr, *bufX0 = nullptr, *bufM = nullptr;
+  uint16_t *bufH0 = nullptr, *bufH1 = nullptr, *bufX1 = nullptr, *bufQ0 = nullptr, *bufQ1 = nullptr;
+  std::vector<StageLaunch> plan;
+  int last_launches = 0;
+  // pinned/device staging for the host entry
+  float* d_in = nullptr; float* d_nmap = nullptr; float* d_out = nullptr;
+  size_t d_in_bytes = 0, d_nmap_bytes = 0, d_out_bytes = 0;
+};
+
+static void build_specs(bsvd_handle* h) {
+  // DenBlock (bsvd_arch.py:325-396), BSVD-64: chns 64/128/256; temp1 4->64, temp2 64->3.
+  for (int blk = 0; blk < 2; ++blk) {
+    StageSpec* s = nullptr;
+    auto S = [&](int l) -> StageSpec& { return h->stages[blk * 16 + l].spec; };
+    const int c0 = h->cfg.chns[0], c1 = h->cfg.chns[1], c2 = h->cfg.chns[2];
+    const int in_ch = blk == 0 ? h->cfg.in_ch : h->cfg.mid_ch;
+    const int out_ch = blk == 0 ? h->cfg.mid_ch : h->cfg.out_ch;
+    (void)s;
+    S(0) = StageSpec(); S(0).cin = in_ch; S(0).cout = h->cfg.interm_ch; S(0).relu6 = true;
+    S(0).first_im2col = (blk == 0);
+    S(1) = StageSpec(); S(1).cin = h->cfg.interm_ch; S(1).cout = c0; S(1).relu6 = true;
+    S(2) = StageSpec(); S(2).cin = c0; S(2).cout = c1; S(2).stride = 2; S(2).relu6 = true; S(2).shift = true;
+    S(3) = StageSpec(); S(3).cin = c1; S(3).cout = c1; S(3).relu6 = true; S(3).shift = true;
+    S(4) = StageSpec(); S(4).cin = c1; S(4).cout = c1; S(4).relu6 = true;
+    S(5) = StageSpec(); S(5).cin = c1; S(5).cout = c2; S(5).stride = 2; S(5).relu6 = true; S(5).shift = true;
+    S(6) = StageSpec(); S(6).cin = c2; S(6).cout = c2; S(6).relu6 = true; S(6).shift = true;
+    S(7) = StageSpec(); S(7).cin = c2; S(7).cout = c2; S(7).relu6 = true; S(7).shift = true;
+    S(8) = StageSpec(); S(8).cin = c2; S(8).cout = c2; S(8).relu6 = true; S(8).shift = true;
+    S(9) = StageSpec(); S(9).cin = c2; S(9).cout = c2; S(9).relu6 = true;
+    S(10) = StageSpec(); S(10).cin = c2; S(10).cout = c1 * 4; S(10).pixshuf = true; S(10).skip = true; S(10).shift = true;
+    S(11) = StageSpec(); S(11).cin = c1; S(11).cout = c1; S(11).relu6 = true; S(11).shift = true;
+    S(12) = StageSpec(); S(12).cin = c1; S(12).cout = c1; S(12).relu6 = true;
+    S(13) = StageSpec(); S(13).cin = c1; S(13).cout = c0 * 4; S(13).pixshuf = true; S(13).skip = true;
+    S(14) = StageSpec(); S(14).cin = c0; S(14).cout = c0; S(14).relu6 = true;
+    S(15) = StageSpec(); S(15).cin = c0; S(15).cout = out_ch;
+    S(15).resid_in = (blk == 0); S(15).final_out = (blk == 1);
+    for (int l = 0; l < 16; ++l) S(l).derive();
+  }
+}
+
+static void free_workspace(bsvd_handle* h) {
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr; h->ws_bytes = 0; h->plan.clear();
+  h->pT = h->pH = h->pW = 0;
+}
+
+// Clip-mode schedule: layer by layer over all T frames (the TSN order; identical arithmetic to the
+// streaming order), temporal folds exchanged through shifted stores.
+static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, float* out, int T,
+                           int in_c, int H, int W) {
+  const bool same_shape = (h->pT == T && h->pH == H && h->pW == W && h->ws);
+  if (same_shape && h->p_in == in && h->p_nmap == nmap && h->p_out == out && h->p_inc == in_c &&
+      !h->plan.empty())
+    return 0;
+  if (!same_shape) {
+    free_workspace(h);
+    const size_t full = (size_t)T * H * W * 64 * 2;
+    const size_t half = (size_t)T * (H / 2) * (W / 2) * 128 * 2;
+    const size_t quar = (size_t)T * (H / 4) * (W / 4) * 256 * 2;
+    const size_t fa = align_up(full, 1024), ha = align_up(half, 1024), qa = align_up(quar, 1024);
+    h->ws_bytes = 4 * fa + 3 * ha + 2 * qa;
+    CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
+    uint8_t* b = reinterpret_cast<uint8_t*>(h->ws);
+    h->bufP = (uint16_t*)b; b += fa;
+    h->bufA = (uint16_t*)b; b += fa;
+    h->bufX0 = (uint16_t*)b; b += fa;
+    h->bufM = (uint16_t*)b; b += fa;
+    h->bufH0 = (uint16_t*)b; b += ha;
+    h->bufH1 = (uint16_t*)b; b += ha;
+    h->bufX1 = (uint16_t*)b; b += ha;
+    h->bufQ0 = (uint16_t*)b; b += qa;
+    h->bufQ1 = (uint16_t*)b; b += qa;
+    h->pT = T; h->pH = H; h->pW = W;
+  }
+  h->p_in = in; h->p_nmap = nmap; h->p_out = out; h->p_inc = in_c;
+  h->plan.assign(BSVD_NUM_LAYERS, StageLaunch());
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+  const long long fs_full = (long long)H * W * 64, fs_half = (long long)H2 * W2 * 128;
+  for (int blk = 0; blk < 2; ++blk) {
+    auto plan = [&](int l, const void* src, int sh, int sw, void* dst, const void* skip = nullptr,
+                    int skip_C = 0, long long skip_fs = 0) -> int {
+      StageIO io;
+      io.in = src; io.T = T; io.H = sh; io.W = sw; io.out = dst;
+      io.skip = skip; io.skip_C = skip_C; io.skip_frame_stride = skip_fs;
+      if (blk == 0 && l == 15) { io.resid_in = in; io.resid_C = in_c; }
+      return plan_stage(h->stages[blk * 16 + l], io, h->bf16, 0, &h->plan[blk * 16 + l]);
+    };
+    const void* src0 = (blk == 0) ? (const void*)h->bufP : (const void*)h->bufM;
+    int rc = 0;
+    rc |= plan(0, src0, H, W, h->bufA);
+    rc |= plan(1, h->bufA, H, W, h->bufX0);
+    rc |= plan(2, h->bufX0, H, W, h->bufH0);
+    rc |= plan(3, h->bufH0, H2, W2, h->bufH1);
+    rc |= plan(4, h->bufH1, H2, W2, h->bufX1);
+    rc |= plan(5, h->bufX1, H2, W2, h->bufQ0);
+    rc |= plan(6, h->bufQ0, H4, W4, h->bufQ1);
+    rc |= plan(7, h->bufQ1, H4, W4, h->bufQ0);
+    rc |= plan(8, h->bufQ0, H4, W4, h->bufQ1);
+    rc |= plan(9, h->bufQ1, H4, W4, h->bufQ0);
+    rc |= plan(10, h->bufQ0, H4, W4, h->bufH0, h->bufX1, 128, fs_half);
+    rc |= plan(11, h->bufH0, H2, W2, h->bufH1);
+    rc |= plan(12, h->bufH1, H2, W2, h->bufH0);
+    rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, 64, fs_full);
+    rc |= plan(14, h->bufA, H, W, h->bufP);
+    if (blk == 0) rc |= plan(15, h->bufP, H, W, h->bufM);
+    else rc |= plan(15, h->bufP, H, W, out, h->bufM, 64, fs_full);
+    if (rc) { h->plan.clear(); return 1; }
+  }
+  return 0;
+}
+
+static int check_hw(int T, int in_c, int H, int W, bool has_nmap) {
+  if (T < 1) return fail("T must be >= 1");
+  if (H < 4 || W < 4 || (H % 4) || (W % 4))
+    return fail("H and W must be multiples of 4 (got %dx%d); the reference fails at the skip add "
+                "(bsvd_arch.py:402-406)", H, W);
+  if (!((in_c == 4 && !has_nmap) || (in_c == 3 && has_nmap)))
+    return fail("input must have 4 channels, or 3 channels plus a noise map (got in_c=%d, "
+                "noise_map=%d)", in_c, (int)has_nmap);
+  return 0;
+}
+
+extern "C" {
+
+const char* bsvd_last_error(void) { return g_err.c_str(); }
+const char* bsvd_version(void) { return "bsvd_b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
+  if (!cfg || !out) return fail("null argument");
+  if (!(cfg->chns[0] == 64 && cfg->chns[1] == 128 && cfg->chns[2] == 256 && cfg->mid_ch == 64 &&
+        cfg->interm_ch == 64 && cfg->in_ch == 4 && cfg->out_ch == 3 && cfg->act_relu6 == 1 &&
+        cfg->norm_none == 1))
+    return fail("only the BSVD-64 configuration of options/test/bsvd_c64.yml is implemented on the "
+                "GPU path (chns=[64,128,256], mid_ch=64, interm_ch=64, in_ch=4, out_ch=3, "
+                "norm='none', act='relu6'); there is no CPU fallback");
+  if (cfg->precision != BSVD_PREC_FP16 && cfg->precision != BSVD_PREC_BF16)
+    return fail("unknown precision %d", cfg->precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: this library only runs on a B200 (sm_100a); no CPU fallback");
+  if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+  int dev = 0, major = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail("device compute capability %d.x is not sm_100a (B200)", major);
+  bsvd_handle* h = new bsvd_handle();
+  h->cfg = *cfg;
+  h->bf16 = (cfg->precision == BSVD_PREC_BF16);
+  build_specs(h);
+  *out = h;
+  return 0;
+}
+
+int bsvd_destroy(bsvd_handle* h) {
+  if (!h) return 0;
+  free_workspace(h);
+  for (auto& s : h->stages) free_stage(s);
+  if (h->d_in) cudaFree(h->d_in);
+  if (h->d_nmap) cudaFree(h->d_nmap);
+  if (h->d_out) cudaFree(h->d_out);
+  delete h;
+  return 0;
+}
+
+int bsvd_layer_shape(const bsvd_handle* h, int layer, int* out_ch, int* in_ch, int* stride) {
+  if (!h || layer < 0 || layer >= BSVD_NUM_LAYERS) return fail("bad layer index %d", layer);
+  const StageSpec& s = h->stages[layer].spec;
+  if (out_ch) *out_ch = s.cout;
+  if (in_ch) *in_ch = s.cin;
+  if (stride) *stride = s.stride;
+  return 0;
+}
+
+int bsvd_set_weights(bsvd_handle* h, int layer, const float* w, const float* bias, int out_ch,
+                     int in_ch) {
+  if (!h || layer < 0 || layer >= BSVD_NUM_LAYERS) return fail("bad layer index %d", layer);
+  if (!w) return fail("null weight pointer");
+  StageDev& sd = h->stages[layer];
+  if (sd.spec.cout != out_ch || sd.spec.cin != in_ch)
+    return fail("layer %d expects weight [%d,%d,3,3], got [%d,%d,3,3]", layer, sd.spec.cout,
+                sd.spec.cin, out_ch, in_ch);
+  return upload_stage(sd, w, bias, h->bf16);
+}
+
+int bsvd_last_launch_count(const bsvd_handle* h) { return h ? h->last_launches : 0; }
+size_t bsvd_workspace_bytes(const bsvd_handle* h) { return h ? h->ws_bytes : 0; }
+
+int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
+                      int in_c, int H, int W, void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  if (check_hw(T, in_c, H, W, noise_map != nullptr)) return 1;
+  for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
+    if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
+  if (build_clip_plan(h, in, noise_map, out, T, in_c, H, W)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long npix = (long long)T * H * W;
+  const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
+  if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
+  else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
+  CUDA_TRY(cudaGetLastError());
+  int launches = 1;
+  for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
+    if (launch_stage(h->plan[l], st)) return 1;
+    ++launches;
+  }
+  h->last_launches = launches;
+  return 0;
+}
+
+static int ensure_dev(float** p, size_t* cur, size_t need) {
+  if (*cur >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cur = 0;
+  CUDA_TRY(cudaMalloc((void**)p, need));
+  *cur = need;
+  return 0;
+}
+
+int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nmap_host,
+                           float* out_host, int T, int in_c, int H, int W, void* stream) {
+  if (!h || !in_host || !out_host) return fail("null argument");
+  if (check_hw(T, in_c, H, W, nmap_host != nullptr)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t plane = (size_t)H * W * sizeof(float);
+  if (ensure_dev(&h->d_in, &h->d_in_bytes, plane * T * in_c)) return 1;
+  if (ensure_dev(&h->d_out, &h->d_out_bytes, plane * T * 3)) return 1;
+  if (nmap_host && ensure_dev(&h->d_nmap, &h->d_nmap_bytes, plane * T)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(h->d_in, in_host, plane * T * in_c, cudaMemcpyHostToDevice, st));
+  if (nmap_host)
+    CUDA_TRY(cudaMemcpyAsync(h->d_nmap, nmap_host, plane * T, cudaMemcpyHostToDevice, st));
+  if (bsvd_forward_clip(h, h->d_in, nmap_host ? h->d_nmap : nullptr, h->d_out, T, in_c, H, W,
+                        stream))
+    return 1;
+  CUDA_TRY(cudaMemcpyAsync(out_host, h->d_out, plane * T * 3, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map, float* out,
+                     int in_c, int H, int W, int* produced, void* stream) {
+  (void)h; (void)frame; (void)noise_map; (void)out; (void)in_c; (void)H; (void)W; (void)stream;
+  if (produced) *produced = 0;
+  return fail("bsvd_stream_push: streaming schedule not built yet");
+}
+
+int bsvd_reset(bsvd_handle* h) {
+  if (!h) return fail("null handle");
+  return 0;
+}
+
+// ---- single-stage hook -------------------------------------------------------------------------
+int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, const float* bias,
+                    const void* skip, void* out, void* stream) {
+  if (!d || !in || !w || !out) return fail("null argument");
+  if (d->cin % 64 || d->cin > 256) return fail("cin must be 64, 128 or 256");
+  if (!(d->cout == 64 || d->cout == 128 || d->cout == 256 || d->cout == 512))
+    return fail("cout must be 64, 128, 256 or 512");
+  StageDev sd;
+  StageSpec& s = sd.spec;
+  s.cin = d->cin; s.cout = d->cout;
+  s.stride = (d->flags & BSVD_EPI_STRIDE2) ? 2 : 1;
+  s.relu6 = d->flags & BSVD_EPI_RELU6;
+  s.pixshuf = d->flags & BSVD_EPI_PIXSHUF;
+  s.skip = d->flags & BSVD_EPI_SKIP_ADD;
+  s.shift = d->flags & BSVD_EPI_SHIFT_STORE;
+  if (s.pixshuf && s.stride == 2) return fail("pixel shuffle and stride 2 cannot be combined");
+  s.derive();
+  const int bf16 = d->precision == BSVD_PREC_BF16;
+  if (upload_stage(sd, w, bias, bf16)) return 1;
+  StageIO io;
+  io.in = in; io.T = d->T; io.H = d->H; io.W = d->W; io.out = out;
+  const int Ho = d->H / s.stride * (s.pixshuf ? 2 : 1), Wo = d->W / s.stride * (s.pixshuf ? 2 : 1);
+  const int Co = s.pixshuf ? s.cout / 4 : s.cout;
+  io.skip = skip; io.skip_C = Co; io.skip_frame_stride = (long long)Ho * Wo * Co;
+  StageLaunch L;
+  int rc = plan_stage(sd, io, bf16, d->debug_variant, &L);
+  if (!rc) rc = launch_stage(L, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  free_stage(sd);
+  if (!rc && e != cudaSuccess) return fail("conv stage failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,558 @@
+// conv_tc.cuh — fused 3x3 convolution stage on sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// One kernel family covers every conv of BSVD-64 (reference: nn.Conv2d call sites
+// bsvd_arch.py:31-38, 208-213, 238-239, 265, 295-298) together with what the reference runs as
+// separate elementwise kernels around it: bias, ReLU6 (:185-192), PixelShuffle (:266), the skip
+// add (:402-406), the residual (:408-414) and the bidirectional-buffer channel shift (:42-50).
+//
+// Formulation: implicit GEMM, im2col-free.
+//   M = 128 consecutive output pixels of one image row (one tcgen05.mma, cta_group::1, M=128)
+//   N = NTILE output channels
+//   K = 9 taps x Cin, walked as (64-channel chunk) x (tap) x (4 k-steps of 16)
+// Activations live in HBM as NHWC 16-bit, so a pixel's 64-channel chunk is one 128-byte row of
+// the SWIZZLE_128B K-major canonical layout.  Stride-1 convs stage ONE haloed tile
+// [(R+2) rows][130 px][64 ch] per chunk with a single TMA box (out-of-bounds = conv zero padding)
+// and form the nine shifted A operands purely by offsetting the UMMA descriptor start address by
+// (dy*130+dx)*128 bytes — no im2col, no re-load.  Stride-2 convs load one box per tap from a 5-D
+// space-to-depth view of the same NHWC tensor.  Weights are pre-swizzled on the host and
+// streamed with 1-D bulk copies (or kept resident when the whole filter bank fits).
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      TMA producer          warp 1      MMA issuer + TMEM allocator
+//   warps 2..5  epilogue (TMEM -> registers -> bias/act/skip/residual -> 128-bit global stores)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace bsvd {
+
+constexpr int kRunPx = 128;        // pixels per MMA row-run (UMMA M)
+constexpr int kChunk = 64;         // channels per K chunk (128 B of 16-bit)
+constexpr int kHaloPx = kRunPx + 2;
+constexpr int kRowBytes = kHaloPx * 128;   // one haloed image row of one chunk: 16640 B
+constexpr int kMaxStages = 12;
+constexpr int kThreads = 192;
+
+enum : int {
+  EPI_RELU6 = 1,
+  EPI_PIXSHUF = 2,
+  EPI_SKIP = 4,
+  EPI_SHIFT = 8,
+  EPI_RESID_IN = 16,    // temp1 outc.3: out[:, :3] = raw_in[:, :3] - out[:, :3]
+  EPI_FINAL = 32,       // temp2 outc.3: fp32 NCHW out = skip[:, :3] - conv[:, :3]
+  EPI_BF16 = 64,        // 16-bit storage type is bf16 (else fp16)
+  EPI_ZERO_FUTURE = 128 // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
+};
+
+struct ConvParams {
+  // ---- problem geometry (OUTPUT grid of the conv, before PixelShuffle) ----
+  int T, H, W;
+  int cin_chunks;       // Cin / 64
+  int n_tiles;          // GEMM N / NTILE
+  int tap_begin, tap_end;
+  int xblocks, yblocks; // ceil(W/128), ceil(H/R)
+  int total_tiles;
+  int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2)
+  int cin_total;        // Cin (stride-2 coordinate math)
+  // ---- pipeline ----
+  int a_stages, w_stages;
+  uint32_t a_stage_bytes, w_stage_bytes;   // stage strides in smem (multiples of 1024)
+  uint32_t a_tx_bytes;                     // bytes one A-stage TMA box delivers
+  int w_resident;
+  int desc_variant;     // 0 production; 1 = base_offset from address (experiment)
+  // ---- operands ----
+  const void* wpack;    // [n_tile][chunk][tap][NTILE][64] 16-bit, rows pre-swizzled (SW128)
+  const float* bias;    // [GEMM N]
+  // ---- epilogue ----
+  int flags;
+  void* out;            // 16-bit NHWC, or fp32 NCHW for EPI_FINAL
+  void* out_prev;       // streaming: frame t-1 / t+1 slots (clip mode: unused)
+  void* out_next;
+  int ring_mode;        // 1 = use out_prev/out_next pointers (T must be 1)
+  int out_C, out_H, out_W;
+  long long out_frame_stride;   // elements
+  const void* skip;     // 16-bit NHWC with the output's shape (EPI_SKIP) / temp1 output (EPI_FINAL)
+  long long skip_frame_stride;
+  int skip_C;
+  const float* resid_in;   // fp32 NCHW raw network input (EPI_RESID_IN)
+  int resid_C;
+  int fold;             // shift fold size in output channels (EPI_SHIFT)
+};
+
+// --------------------------------------------------------------------------------------------
+// PTX helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((++spins & 0x3ff) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();   // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes,
+                                          uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr, int variant) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);          // [0,14)  start address >> 4
+  d |= static_cast<uint64_t>(1) << 16;                          // [16,30) LBO (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // [32,46) SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;                          // [46,48) descriptor version (sm_100)
+  if (variant == 1) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;   // [49,52) base offset
+  d |= static_cast<uint64_t>(2) << 61;                          // [61,64) SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=fp16|bf16, both K-major, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int bf16) {
+  return (1u << 4) | (static_cast<uint32_t>(bf16) << 7) | (static_cast<uint32_t>(bf16) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRunPx >> 4) << 24);
+}
+
+__device__ __forceinline__ float relu6f(float x) { return fminf(fmaxf(x, 0.f), 6.f); }
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (BF16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float load16(const void* p, long long idx) {
+  if constexpr (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+  else return __half2float(reinterpret_cast<const __half*>(p)[idx]);
+}
+
+// --------------------------------------------------------------------------------------------
+// Epilogue for one group of 8 consecutive GEMM columns of one pixel.
+// --------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ void epilogue_vec8(const ConvParams& p, float (&f)[8], int n0, int t,
+                                              int y, int x) {
+  const int flags = p.flags;
+  int c0 = n0, oy = y, ox = x;
+  if (flags & EPI_PIXSHUF) {
+    // GEMM columns are ordered (subpixel q = 2i+j, channel c): conv channel c*4+q -> out[c, 2y+i, 2x+j]
+    const int q = n0 / p.out_C;
+    c0 = n0 - q * p.out_C;
+    oy = 2 * y + (q >> 1);
+    ox = 2 * x + (q & 1);
+  }
+  const long long pix = static_cast<long long>(oy) * p.out_W + ox;
+  if (flags & EPI_SKIP) {
+    const uint4 s = *reinterpret_cast<const uint4*>(
+        reinterpret_cast<const uint16_t*>(p.skip) + t * p.skip_frame_stride + pix * p.skip_C + c0);
+    float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
+           d = unpack2<BF16>(s.w);
+    f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+    f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
+  }
+  if (flags & EPI_RELU6) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = relu6f(f[i]);
+  }
+  if ((flags & EPI_RESID_IN) && n0 == 0) {
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    const float* r = p.resid_in + (static_cast<long long>(t) * p.resid_C) * plane +
+                     static_cast<long long>(y) * p.W + x;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+  }
+  uint4 v;
+  v.x = pack2<BF16>(f[0], f[1]);
+  v.y = pack2<BF16>(f[2], f[3]);
+  v.z = pack2<BF16>(f[4], f[5]);
+  v.w = pack2<BF16>(f[6], f[7]);
+  const long long off = pix * p.out_C + c0;
+  uint16_t* base = reinterpret_cast<uint16_t*>(p.out);
+  if (!(flags & EPI_SHIFT)) {
+    *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = v;
+    return;
+  }
+  // Bidirectional-buffer shift folded into the store (ShiftConv.forward, bsvd_arch.py:42-50):
+  // the consumer conv of frame u reads channels [0,f) of frame u+1 and [f,2f) of frame u-1, so the
+  // producer of frame t writes those folds straight into the tensors of frames t-1 / t+1.
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  if (c0 < p.fold) {
+    if (p.ring_mode) {
+      if (p.out_prev) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_prev) + off) = v;
+      if (flags & EPI_ZERO_FUTURE) *reinterpret_cast<uint4*>(base + off) = zero;
+    } else {
+      if (t > 0) *reinterpret_cast<uint4*>(base + (t - 1) * p.out_frame_stride + off) = v;
+      if (t == p.T - 1) *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = zero;
+    }
+  } else if (c0 < 2 * p.fold) {
+    if (p.ring_mode) {
+      if (p.out_next) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_next) + off) = v;
+      if (!p.out_prev) *reinterpret_cast<uint4*>(base + off) = zero;   // first frame of a stream
+    } else {
+      if (t + 1 < p.T) *reinterpret_cast<uint4*>(base + (t + 1) * p.out_frame_stride + off) = v;
+      if (t == 0) *reinterpret_cast<uint4*>(base + off) = zero;
+    }
+  } else {
+    *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = v;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// The kernel
+// --------------------------------------------------------------------------------------------
+struct TileCoord {
+  int nt, t, y0, x0;
+};
+template <int R>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord c;
+  c.nt = tile % p.n_tiles;
+  int s = tile / p.n_tiles;
+  int xb = s % p.xblocks;
+  s /= p.xblocks;
+  int yb = s % p.yblocks;
+  c.t = s / p.yblocks;
+  c.y0 = yb * R;
+  c.x0 = xb * kRunPx;
+  return c;
+}
+
+template <int NTILE, int R>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ ConvParams p) {
+  static_assert(NTILE == 16 || NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
+  constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator buffer
+  constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // 1024-byte aligned operand area (swizzle pattern anchor)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t w_base = a_base + p.a_stages * p.a_stage_bytes;
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (3 * kMaxStages + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (4 * kMaxStages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (4 * kMaxStages + 2 + b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int ntaps = p.tap_end - p.tap_begin;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<R>(p, tile);
+        for (int c = 0; c < p.cin_chunks; ++c) {
+          if (p.mode == 0) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            mbar_expect_tx(a_full(sa), p.a_tx_bytes);
+            tma_load_4d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
+                        tc.y0 - 1, tc.t);
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+          }
+          for (int tap = p.tap_begin; tap < p.tap_end; ++tap) {
+            if (p.mode == 1) {
+              // stride 2: input (2y+dy-1, 2x+dx-1) seen through the [T][H/2][2][W/2][2*C] view
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const int px = (dx == 1) ? 0 : 1, x2 = tc.x0 + ((dx == 0) ? -1 : 0);
+              const int py = (dy == 1) ? 0 : 1, y2 = tc.y0 + ((dy == 0) ? -1 : 0);
+              mbar_wait(a_empty(sa), pa ^ 1);
+              mbar_expect_tx(a_full(sa), p.a_tx_bytes);
+              tma_load_5d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
+                          px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
+              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            }
+            if (!p.w_resident || first) {
+              mbar_wait(w_empty(sw), pw ^ 1);
+              mbar_expect_tx(w_full(sw), p.w_stage_bytes);
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
+                  (static_cast<size_t>(tc.nt * p.cin_chunks + c) * ntaps + (tap - p.tap_begin)) *
+                      p.w_stage_bytes;
+              bulk_load(w_base + sw * p.w_stage_bytes, src, p.w_stage_bytes, w_full(sw));
+              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(NTILE, (p.flags & EPI_BF16) ? 1 : 0);
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(acc_empty(buf), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+        for (int c = 0; c < p.cin_chunks; ++c) {
+          if (p.mode == 0) {
+            mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+          }
+          for (int tap = p.tap_begin; tap < p.tap_end; ++tap) {
+            if (p.mode == 1) {
+              mbar_wait(a_full(sa), pa);
+            }
+            if (!p.w_resident || it == 0) mbar_wait(w_full(sw), pw);
+            tc_fence_after();
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
+            const uint32_t w_stage = w_base + sw * p.w_stage_bytes;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const uint32_t a_row = (p.mode == 0)
+                  ? a_stage + static_cast<uint32_t>((r + dy) * kHaloPx + dx) * 128u
+                  : a_stage + static_cast<uint32_t>(r) * (kRunPx * 128u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_kmajor_sw128_desc(a_row + k * 32u, p.desc_variant);
+                const uint64_t bd = make_kmajor_sw128_desc(w_stage + k * 32u, 0);
+                const uint32_t acc = (c > 0 || tap > p.tap_begin || k > 0) ? 1u : 0u;
+                umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, acc);
+              }
+            }
+            if (p.w_resident) {
+              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+            } else {
+              umma_commit(w_empty(sw));
+              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+            }
+            if (p.mode == 1) {
+              umma_commit(a_empty(sa));
+              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (p.mode == 0) {
+            umma_commit(a_empty(sa));
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // pixel offset inside the 128-px run
+    const bool bf16 = (p.flags & EPI_BF16) != 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile<R>(p, tile);
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(acc_full(buf), acc_phase);
+      tc_fence_after();
+      const int x = tc.x0 + row;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        const int y = tc.y0 + r;
+        const bool valid = (x < p.W) && (y < p.H);
+        constexpr int LDW = (NTILE >= 32) ? 32 : 16;
+#pragma unroll 1
+        for (int g = 0; g < NTILE / LDW; ++g) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                 buf * kAccCols + r * NTILE + g * LDW;
+          if constexpr (LDW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int nbase = tc.nt * NTILE + g * LDW;
+            if (p.flags & EPI_FINAL) {
+              // temp2 outc.3 + residual (bsvd_arch.py:394, 408-414): out = temp1_out[:, :3] - conv[:, :3]
+              if (g == 0) {
+                const long long plane = static_cast<long long>(p.H) * p.W;
+                const long long pix = static_cast<long long>(y) * p.W + x;
+                float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane + pix;
+                const long long sidx = tc.t * p.skip_frame_stride + pix * p.skip_C;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  const float s = bf16 ? load16<true>(p.skip, sidx + i) : load16<false>(p.skip, sidx + i);
+                  o[i * plane] = s - (__uint_as_float(v[i]) + __ldg(p.bias + i));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < LDW / 8; ++j) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  f[i] = __uint_as_float(v[j * 8 + i]) + __ldg(p.bias + nbase + j * 8 + i);
+                if (bf16) epilogue_vec8<true>(p, f, nbase + j * 8, tc.t, y, x);
+                else epilogue_vec8<false>(p, f, nbase + j * 8, tc.t, y, x);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+}  // namespace bsvd

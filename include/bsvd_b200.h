@@ -1,0 +1,135 @@
+/*
+ * bsvd_b200.h — C ABI of the B200-native BSVD-64 inference path.
+ *
+ * This is the drop-in boundary for ONE hot path of ChenyangQiQi/BSVD:
+ *   Experimental_root/archs/bsvd_arch.py::BSVD.forward          (bsvd_arch.py:490-499)
+ *   -> streaming_forward / feedin_one_element / DenBlock.forward (bsvd_arch.py:501-552, 485-488, 374-396)
+ * Plain pointers and sizes only; no torch types.  The reference-side binding is the
+ * ctypes stub in bsvd_b200/capi.py; the nn.Module that registers under
+ * ARCH_REGISTRY['BSVD'] (bsvd_b200/arch.py) calls nothing but these entry points.
+ *
+ * All device pointers are plain CUDA device pointers in the current context.  `stream` is a
+ * cudaStream_t passed as void* (0 = legacy default stream).  Every call returns 0 on success,
+ * non-zero on failure; bsvd_last_error() returns a description of the last failure of the
+ * calling thread.  Nothing here ever falls back to a CPU path.
+ */
+#ifndef BSVD_B200_H_
+#define BSVD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsvd_handle bsvd_handle;
+
+/* Operand precision of the tensor-core contractions (accumulation is always fp32,
+ * bias/activation/residual arithmetic is fp32, activations are stored in this type). */
+enum { BSVD_PREC_FP16 = 0, BSVD_PREC_BF16 = 1 };
+
+/* Mirrors the constructor kwargs of BSVD (bsvd_arch.py:446-447) as passed by
+ * options/test/bsvd_c64.yml:85-93.  Only the BSVD-64 configuration is implemented on the GPU:
+ * chns={64,128,256}, mid_ch=64, interm_ch=64, in_ch=4, out_ch=3, norm='none', act='relu6'.
+ * Anything else makes bsvd_create fail (there is no CPU fallback). */
+typedef struct bsvd_config {
+  int chns[3];
+  int mid_ch;
+  int interm_ch;
+  int in_ch;
+  int out_ch;
+  int act_relu6;   /* 1 = relu6 (only supported value) */
+  int norm_none;   /* 1 = norm 'none' (only supported value) */
+  int precision;   /* BSVD_PREC_* */
+  int device;      /* CUDA device ordinal, -1 = current */
+} bsvd_config;
+
+#define BSVD_NUM_LAYERS 32 /* 16 convs per DenBlock x 2 DenBlocks (bsvd_arch.py:325-396) */
+
+/* -- lifetime ---------------------------------------------------------------------------- */
+/* replaces BSVD.__init__ (bsvd_arch.py:446-456) */
+int bsvd_create(const bsvd_config* cfg, bsvd_handle** out);
+/* replaces nn.Module teardown */
+int bsvd_destroy(bsvd_handle* h);
+const char* bsvd_last_error(void);
+/* library / build information, e.g. "bsvd_b200 0.1 sm_100a" */
+const char* bsvd_version(void);
+
+/* -- weights -------------------------------------------------------------------------------
+ * replaces BSVD.load / DenBlock.load_from (bsvd_arch.py:462-474, 349-355).
+ * layer = block*16 + l, block 0 = temp1, 1 = temp2, l in reference execution order:
+ *   0 inc.convblock.0      1 inc.convblock.3        2 downc0.convblock.0 (stride 2)
+ *   3 downc0.memconv.c1    4 downc0.memconv.c2      5 downc1.convblock.0 (stride 2)
+ *   6 downc1.memconv.c1    7 downc1.memconv.c2      8 upc2.memconv.c1
+ *   9 upc2.memconv.c2     10 upc2.convblock.0 (+PixelShuffle)
+ *  11 upc1.memconv.c1     12 upc1.memconv.c2       13 upc1.convblock.0 (+PixelShuffle)
+ *  14 outc.convblock.0    15 outc.convblock.3
+ * w is the nn.Conv2d weight, HOST pointer, fp32, OIHW contiguous; bias HOST fp32 [O].
+ * The call repacks into the tensor-core layout and uploads (synchronous). */
+int bsvd_set_weights(bsvd_handle* h, int layer, const float* w_oihw, const float* bias,
+                     int out_ch, int in_ch);
+/* expected (out_ch, in_ch) of a layer; returns non-zero for a bad index */
+int bsvd_layer_shape(const bsvd_handle* h, int layer, int* out_ch, int* in_ch, int* stride);
+
+/* -- clip mode: BSVD.forward on one stream of T frames (bsvd_arch.py:490-552) ---------------
+ * in:        device fp32 [T, in_c, H, W] contiguous, in_c = 4, or in_c = 3 with noise_map
+ * noise_map: device fp32 [T, 1, H, W] or NULL   (the torch.cat of bsvd_arch.py:492-493 is folded in)
+ * out:       device fp32 [T, 3, H, W]
+ * H and W must be multiples of 4 (the reference raises at the skip add otherwise).
+ * Work is enqueued on `stream`; no host synchronisation. Equivalent to feeding the T frames
+ * through streaming_forward (same zero folds at both clip ends). */
+int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out,
+                      int T, int in_c, int H, int W, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, then waits for
+ * completion.  This is the end-to-end entry the bench's `e2e` number goes through. */
+int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* noise_map_host,
+                           float* out_host, int T, int in_c, int H, int W, void* stream);
+
+/* -- streaming mode: BSVD.feedin_one_element / reset (bsvd_arch.py:485-488, 459-461) -------
+ * frame:     device fp32 [in_c, H, W] or NULL (NULL = the reference's feedin_one_element(None))
+ * noise_map: device fp32 [1, H, W] or NULL
+ * out:       device fp32 [3, H, W]; written iff *produced is set to 1
+ * The first 16 pushes of a stream produce nothing (count_shift, bsvd_arch.py:554-560). */
+int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map, float* out,
+                     int in_c, int H, int W, int* produced, void* stream);
+int bsvd_reset(bsvd_handle* h);
+
+/* -- introspection used by bench.py / tests -------------------------------------------------- */
+/* number of kernel launches enqueued by the last forward/push on this handle */
+int bsvd_last_launch_count(const bsvd_handle* h);
+/* bytes of device workspace currently held */
+size_t bsvd_workspace_bytes(const bsvd_handle* h);
+
+/* -- single fused conv stage (test / micro-benchmark hook) ------------------------------------
+ * Runs ONE fused 3x3 conv stage exactly as the network does (same kernels), on NHWC
+ * 16-bit activations.  Used by tests/ to check every kernel variant against the oracle.
+ * Flags describe the prologue/epilogue that the reference expresses as separate ops. */
+enum {
+  BSVD_EPI_RELU6 = 1,        /* nn.ReLU6                               (bsvd_arch.py:185-192)  */
+  BSVD_EPI_PIXSHUF = 2,      /* nn.PixelShuffle(2)                     (bsvd_arch.py:266)      */
+  BSVD_EPI_SKIP_ADD = 4,     /* DenBlock.none_add                      (bsvd_arch.py:402-406)  */
+  BSVD_EPI_SHIFT_STORE = 8,  /* BiBufferConv/ShiftConv channel folds   (bsvd_arch.py:42-50)    */
+  BSVD_EPI_STRIDE2 = 16      /* DownBlock conv stride 2                (bsvd_arch.py:238-239)  */
+};
+typedef struct bsvd_conv_desc {
+  int T, H, W;        /* INPUT frames / rows / cols */
+  int cin, cout;      /* conv channels (cout counts conv outputs, i.e. before PixelShuffle) */
+  int flags;          /* BSVD_EPI_* */
+  int precision;      /* BSVD_PREC_* */
+  int debug_variant;  /* 0 = production; other values select descriptor experiments */
+} bsvd_conv_desc;
+/* in:  device 16-bit [T,H,W,cin]; w/bias: HOST fp32 OIHW / [cout];
+ * skip: device 16-bit, shape of the output, or NULL; out: device 16-bit NHWC:
+ *   [T,H,W,cout] | stride2: [T,H/2,W/2,cout] | pixshuf: [T,2H,2W,cout/4]
+ * With SHIFT_STORE the output holds the *shifted* tensor a following BiBufferConv reads:
+ *   out[t][..., 0:f] = y[t+1][..., 0:f], out[t][..., f:2f] = y[t-1][..., f:2f] (zeros off-clip),
+ *   f = channels/8. */
+int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w_oihw,
+                    const float* bias, const void* skip, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSVD_B200_H_ */
