@@ -1,0 +1,320 @@
+"""Drop-in replacement of the reference's streaming denoiser class.
+
+Mirrors Experimental_root/archs/bsvd_arch.py::BSVD (:441-560): same constructor kwargs (the
+`network_g` block of options/test/bsvd_c64.yml:85-93 is splatted into it by
+basicsr.archs.build_network), same parameter names in state_dict() (temp1.inc.convblock.0.weight,
+temp1.downc0.memconv.c1.op.conv.weight, ...), same public methods (forward, streaming_forward,
+feedin_one_element, reset, load, shift_num) and the same None protocol.  All arithmetic runs in
+libbsvd_b200.so through the C ABI (bsvd_b200/capi.py); torch only owns parameters, device buffers
+and the stream.  There is no CPU path: constructing the module for any configuration other than
+BSVD-64, or calling it without a B200 and the built library, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import capi
+
+# execution order inside one DenBlock -> (state-dict stem, TSN-checkpoint stem)
+# (re-keying of BSVD.load / DenBlock.load_from, bsvd_arch.py:143-145, 252-255, 280-282, 349-355)
+_LAYERS = (
+    ("inc.convblock.0", "inc.convblock.0"),
+    ("inc.convblock.3", "inc.convblock.3"),
+    ("downc0.convblock.0", "downc0.convblock.0"),
+    ("downc0.memconv.c1.op.conv", "downc0.convblock.3.c1.net"),
+    ("downc0.memconv.c2.op.conv", "downc0.convblock.3.c2.net"),
+    ("downc1.convblock.0", "downc1.convblock.0"),
+    ("downc1.memconv.c1.op.conv", "downc1.convblock.3.c1.net"),
+    ("downc1.memconv.c2.op.conv", "downc1.convblock.3.c2.net"),
+    ("upc2.memconv.c1.op.conv", "upc2.convblock.0.c1.net"),
+    ("upc2.memconv.c2.op.conv", "upc2.convblock.0.c2.net"),
+    ("upc2.convblock.0", "upc2.convblock.1"),
+    ("upc1.memconv.c1.op.conv", "upc1.convblock.0.c1.net"),
+    ("upc1.memconv.c2.op.conv", "upc1.convblock.0.c2.net"),
+    ("upc1.convblock.0", "upc1.convblock.1"),
+    ("outc.convblock.0", "outc.convblock.0"),
+    ("outc.convblock.3", "outc.convblock.3"),
+)
+
+
+class _Node(nn.Module):
+    """Pure container used to reproduce the reference's dotted parameter names."""
+
+    def forward(self, *a, **k):  # pragma: no cover - never called
+        raise RuntimeError("container module; the arithmetic lives in libbsvd_b200.so")
+
+
+def _attach(root: nn.Module, dotted: str, leaf: nn.Module) -> None:
+    parts = dotted.split(".")
+    node = root
+    for p in parts[:-1]:
+        if p not in node._modules:
+            node.add_module(p, _Node())
+        node = node._modules[p]
+    node.add_module(parts[-1], leaf)
+
+
+def _layer_shapes(block, chns, mid_ch, in_ch, out_ch, interm_ch):
+    c0, c1, c2 = chns
+    cin = in_ch if block == 0 else mid_ch
+    cout = mid_ch if block == 0 else out_ch
+    return [(interm_ch, cin, 1), (c0, interm_ch, 1), (c1, c0, 2), (c1, c1, 1), (c1, c1, 1),
+            (c2, c1, 2), (c2, c2, 1), (c2, c2, 1), (c2, c2, 1), (c2, c2, 1), (c1 * 4, c2, 1),
+            (c1, c1, 1), (c1, c1, 1), (c0 * 4, c1, 1), (c0, c0, 1), (cout, c0, 1)]
+
+
+class BSVD(nn.Module):
+    """Bidirectional-buffer streaming video denoiser, B200-native (see module docstring)."""
+
+    def __init__(self, chns=[32, 64, 128], mid_ch=3, shift_input=False, in_ch=4, out_ch=3,
+                 norm='bn', act='relu', interm_ch=30, blind=False,
+                 pretrain_ckpt='./experiments/pretrained_ckpt/bsvd-64.pth', precision=None):
+        super().__init__()
+        chns = list(chns)
+        if not (chns == [64, 128, 256] and mid_ch == 64 and interm_ch == 64 and in_ch == 4 and
+                out_ch == 3 and norm == 'none' and act == 'relu6' and not shift_input
+                and not blind):
+            raise NotImplementedError(
+                "bsvd_b200 implements the BSVD-64 configuration of options/test/bsvd_c64.yml only "
+                "(chns=[64,128,256], mid_ch=64, interm_ch=64, norm='none', act='relu6', "
+                "shift_input=False, blind=False); there is no CPU/PyTorch fallback")
+        self.cfg = dict(chns=chns, mid_ch=mid_ch, in_ch=in_ch, out_ch=out_ch, interm_ch=interm_ch)
+        self.temp1 = _Node()
+        self.temp2 = _Node()
+        self._param_names = []
+        for blk, root in enumerate((self.temp1, self.temp2)):
+            shapes = _layer_shapes(blk, chns, mid_ch, in_ch, out_ch, interm_ch)
+            for (stem, _tsn), (co, ci, st) in zip(_LAYERS, shapes):
+                conv = nn.Conv2d(ci, co, kernel_size=3, stride=st, padding=1, bias=True)
+                _attach(root, stem, conv)
+                self._param_names.append(f"temp{blk + 1}.{stem}")
+        self.shift_num = 16          # count_shift(): 8 BiBufferConv per DenBlock (bsvd_arch.py:554-560)
+        self.independent_clips = False   # True: forward([N,F,..]) treats the N clips separately
+        self.precision = precision or os.environ.get("BSVD_B200_PRECISION")  # 'fp16' | 'bf16' | None
+        self._handle = None
+        self._handle_prec = None
+        self._weights_sig = None
+        self._stream_out = None
+        self.reset_params()
+        if pretrain_ckpt is not None:
+            self.load(pretrain_ckpt)
+
+    # ---------------------------------------------------------------- parameters / checkpoints
+    @staticmethod
+    def weight_init(m):
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, nonlinearity='relu')   # bsvd_arch.py:476-479
+
+    def reset_params(self):
+        for m in self.modules():
+            self.weight_init(m)
+
+    def _convs(self):
+        mods = dict(self.named_modules())
+        return [mods[n] for n in self._param_names]
+
+    def load(self, path):
+        """BSVD.load (bsvd_arch.py:462-474): {'params': TSN-layout state dict}, optional 'module.'."""
+        ckpt = torch.load(path, map_location="cpu")
+        print("load from %s" % path)
+        self.load_tsn_state(ckpt['params'])
+
+    def load_tsn_state(self, ckpt_state):
+        first = list(ckpt_state.keys())[0]
+        base = 'module.base_model.' if 'module' in first else 'base_model.'
+        convs = self._convs()
+        with torch.no_grad():
+            for blk in range(2):
+                for i, (_stem, tsn) in enumerate(_LAYERS):
+                    k = f"{base}nets_list.{blk}.{tsn}"
+                    conv = convs[blk * 16 + i]
+                    conv.weight.copy_(ckpt_state[k + ".weight"])
+                    conv.bias.copy_(ckpt_state[k + ".bias"])
+        self._weights_sig = None
+
+    # ---------------------------------------------------------------- native handle
+    def _select_precision(self):
+        if self.precision is not None:
+            p = str(self.precision).lower()
+            if p not in ("fp16", "bf16"):
+                raise ValueError("precision must be 'fp16' or 'bf16'")
+            return p
+        w = self.temp1.inc.convblock._modules['0'].weight
+        if w.dtype == torch.bfloat16:
+            return "bf16"
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16:
+            return "bf16"
+        # fp32 weights, fp16 weights (profile.py:79) and fp16 autocast all use fp16 operands with
+        # fp32 accumulation: 11-bit significands, the same operand precision as TF32.
+        return "fp16"
+
+    def _out_dtype(self):
+        w = self.temp1.inc.convblock._modules['0'].weight
+        if torch.is_autocast_enabled():
+            return torch.get_autocast_dtype('cuda')
+        return w.dtype if w.dtype in (torch.float16, torch.bfloat16) else torch.float32
+
+    def _ensure_handle(self, device):
+        lib = capi.load_library()
+        if not torch.cuda.is_available():
+            raise capi.BsvdError("bsvd_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
+        prec = self._select_precision()
+        if self._handle is not None and self._handle_prec != prec:
+            self._destroy()
+        if self._handle is None:
+            cfg = capi.BsvdConfig()
+            cfg.chns[0], cfg.chns[1], cfg.chns[2] = self.cfg["chns"]
+            cfg.mid_ch, cfg.interm_ch = self.cfg["mid_ch"], self.cfg["interm_ch"]
+            cfg.in_ch, cfg.out_ch = self.cfg["in_ch"], self.cfg["out_ch"]
+            cfg.act_relu6, cfg.norm_none = 1, 1
+            cfg.precision = capi.PREC_FP16 if prec == "fp16" else capi.PREC_BF16
+            cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+            h = C.c_void_p()
+            capi.check(lib.bsvd_create(C.byref(cfg), C.byref(h)))
+            self._handle, self._handle_prec, self._weights_sig = h, prec, None
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if sig != self._weights_sig:
+            for i, conv in enumerate(self._convs()):
+                w = conv.weight.detach().float().cpu().contiguous()
+                b = conv.bias.detach().float().cpu().contiguous()
+                capi.check(lib.bsvd_set_weights(self._handle, i, w.data_ptr(), b.data_ptr(),
+                                                w.shape[0], w.shape[1]))
+            self._weights_sig = sig
+        return lib
+
+    def _destroy(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                capi.load_library().bsvd_destroy(self._handle)
+            except Exception:  # noqa: BLE001
+                pass
+            self.__dict__["_handle"] = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def _apply(self, fn, *a, **k):
+        self._weights_sig = None
+        return super()._apply(fn, *a, **k)
+
+    # ---------------------------------------------------------------- clip mode
+    def _run_stream(self, x, noise_map=None):
+        """x: [T,C,H,W] on a CUDA device -> [T,3,H,W] (one continuous stream)."""
+        if not x.is_cuda:
+            x = x.cuda()          # the reference does x.cuda() per frame (bsvd_arch.py:520)
+        dev = x.device
+        with torch.cuda.device(dev):
+            lib = self._ensure_handle(dev)
+            xf = x.detach().float().contiguous()
+            nm = None
+            if noise_map is not None:
+                nm = noise_map.detach().to(dev).float().contiguous()
+            T, Cc, H, W = xf.shape
+            out = torch.empty((T, 3, H, W), dtype=torch.float32, device=dev)
+            capi.check(lib.bsvd_forward_clip(
+                self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
+                out.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+        od = self._out_dtype()
+        return out if od == torch.float32 else out.to(od)
+
+    def forward(self, input, noise_map=None):
+        """[N,F,C,H,W] (+ optional noise_map [N,F,1,H,W]) -> [N,F,3,H,W]  (bsvd_arch.py:490-499).
+        Like the reference, N>1 clips form ONE continuous stream unless `independent_clips`."""
+        N, Fr, Cc, H, W = input.shape
+        if self.independent_clips and N > 1:
+            outs = [self._run_stream(input[n], None if noise_map is None else noise_map[n])
+                    for n in range(N)]
+            return torch.stack(outs, dim=0)
+        nm = None if noise_map is None else noise_map.reshape(N * Fr, 1, H, W)
+        out = self._run_stream(input.reshape(N * Fr, Cc, H, W), nm)
+        return out.reshape(N, Fr, 3, H, W)
+
+    def streaming_forward(self, input_seq):
+        """Pipeline-style inference over a whole sequence (bsvd_arch.py:501-552): list of
+        [1,C,H,W] tensors or one [n,C,H,W] tensor -> [n,3,H,W].  State is reset at entry and exit."""
+        if isinstance(input_seq, (list, tuple)):
+            input_seq = torch.cat([t.cuda() for t in input_seq], dim=0)
+        assert isinstance(input_seq, torch.Tensor), "convert the input into a sequence"
+        self.reset()
+        with torch.no_grad():
+            return self._run_stream(input_seq)
+
+    def denoise_host(self, input_host, noise_map_host=None, out_host=None):
+        """End-to-end entry with HOST buffers (pinned recommended): H2D + forward + D2H inside the
+        C ABI (bsvd_forward_clip_host).  input_host: fp32 [T,C,H,W] CPU tensor -> fp32 [T,3,H,W]."""
+        assert not input_host.is_cuda and input_host.dtype == torch.float32
+        dev = torch.device("cuda", torch.cuda.current_device())
+        lib = self._ensure_handle(dev)
+        x = input_host.contiguous()
+        T, Cc, H, W = x.shape
+        nm = noise_map_host.contiguous() if noise_map_host is not None else None
+        if out_host is None:
+            out_host = torch.empty((T, 3, H, W), dtype=torch.float32).pin_memory()
+        capi.check(lib.bsvd_forward_clip_host(
+            self._handle, x.data_ptr(), nm.data_ptr() if nm is not None else None,
+            out_host.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+        return out_host
+
+    # ---------------------------------------------------------------- streaming mode
+    def feedin_one_element(self, x, noise_map=None):
+        """One pipeline step (bsvd_arch.py:485-488): x [1,C,H,W] or None -> [1,3,H,W] or None.
+        The first `shift_num` (=16) calls of a stream return None."""
+        dev = x.device if x is not None and x.is_cuda else torch.device(
+            "cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            lib = self._ensure_handle(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            produced = C.c_int(0)
+            if x is not None:
+                xf = x.detach().to(dev).float().contiguous()
+                _, Cc, H, W = xf.shape
+                nm = None
+                if noise_map is not None:
+                    nm = noise_map.detach().to(dev).float().contiguous()
+                self._stream_shape = (Cc, H, W)
+                out = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+                capi.check(lib.bsvd_stream_push(
+                    self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
+                    out.data_ptr(), Cc, H, W, C.byref(produced), stream))
+            else:
+                if getattr(self, "_stream_shape", None) is None:
+                    return None
+                Cc, H, W = self._stream_shape
+                out = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+                capi.check(lib.bsvd_stream_push(self._handle, None, None, out.data_ptr(), Cc, H, W,
+                                                C.byref(produced), stream))
+        if not produced.value:
+            return None
+        od = self._out_dtype()
+        return out if od == torch.float32 else out.to(od)
+
+    def reset(self):
+        """Clear all streaming buffers (bsvd_arch.py:459-461)."""
+        self._stream_shape = None
+        if self._handle is not None:
+            capi.check(capi.load_library().bsvd_reset(self._handle))
+
+    def count_shift(self):
+        return self.shift_num
+
+    def extra_repr(self):
+        return "B200-native BSVD-64 (tcgen05/TMEM/TMA fused conv stages), precision=%s" % (
+            self.precision or "auto")
+
+    @property
+    def last_launch_count(self):
+        return 0 if self._handle is None else capi.load_library().bsvd_last_launch_count(
+            self._handle)
+
+
+def params_to_numpy(module: BSVD):
+    return {k: v.detach().float().cpu().numpy().astype(np.float32)
+            for k, v in module.state_dict().items()}

@@ -1,0 +1,83 @@
+"""The CPU oracle against the fixtures generated from the unmodified reference
+(tests/golden/make_golden.py).  Bar: the oracle is the same fp32 arithmetic in a different
+association order at most, so 1e-4 max-abs on trained-like weights (|y| ~ 1), 2e-3 on the
+saturating default-init stress case (|y| ~ 12; the reference's own clip-vs-stream gap there is 2e-5
+and conv summation order differs between its two schedules)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bsvd_oracle as O
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    g = np.load(path)
+    sd = O.make_synthetic_params(int(g["param_seed"]), float(g["weight_scale"]))
+    assert O.params_digest(sd) == str(g["params_digest"]), "synthetic weight stream changed"
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    assert O.params_digest({"x": x}) == str(g["x_digest"]), "synthetic clip stream changed"
+    return g, O.layers_from_tsn_state(sd), x
+
+
+def test_fixtures_present():
+    assert len(GOLDEN) >= 4
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_clip_order_matches_reference(path):
+    g, layers, x = _load(path)
+    y = O.forward_clip(layers, x)
+    tol = 1e-4 if float(g["weight_scale"]) < 1.0 else 2e-3
+    for key in ("y_clip", "y_stream"):
+        d = float((y - torch.from_numpy(g[key])).abs().max())
+        assert d <= tol, (key, d)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_stream_order_matches_reference(path):
+    g, layers, x = _load(path)
+    so = O.StreamOracle(layers)
+    y = so.streaming_forward(x)
+    tol = 1e-4 if float(g["weight_scale"]) < 1.0 else 2e-3
+    assert float((y - torch.from_numpy(g["y_stream"])).abs().max()) <= tol
+    # None protocol of feedin_one_element (bsvd_arch.py:518-547)
+    outs = [so.feedin_one_element(x[i:i + 1]) for i in range(x.shape[0])]
+    calls = x.shape[0]
+    while sum(o is not None for o in outs) < x.shape[0]:
+        outs.append(so.feedin_one_element(None))
+        calls += 1
+    so.reset()
+    first = next(i for i, o in enumerate(outs) if o is not None)
+    assert first == int(g["first_output_call"]) == O.StreamOracle.shift_num == int(g["shift_num"])
+    assert calls == int(g["calls_to_drain"])
+
+
+def test_param_count_and_keys():
+    sd = O.make_synthetic_params(0)
+    assert sum(v.numel() for v in sd.values()) == 9815683   # SURVEY §0 [probe]
+    assert len(O.tsn_keys()) == len(O.bsvd_keys()) == 32
+    g = np.load(GOLDEN[0])
+    assert int(g["n_params"]) == 9815683
+
+
+def test_module_prefix_rekey():
+    sd = O.make_synthetic_params(0)
+    sd2 = {"module." + k: v for k, v in sd.items()}
+    a = O.layers_from_tsn_state(sd)
+    b = O.layers_from_tsn_state(sd2)
+    assert all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) for x, y in zip(a, b))
+
+
+def test_temporal_shift_edges():
+    x = torch.arange(2 * 16 * 1 * 1, dtype=torch.float32).reshape(2, 16, 1, 1) + 1
+    s = O.temporal_shift(x)
+    assert torch.equal(s[0, :2], x[1, :2]) and torch.equal(s[1, :2], torch.zeros(2, 1, 1))
+    assert torch.equal(s[1, 2:4], x[0, 2:4]) and torch.equal(s[0, 2:4], torch.zeros(2, 1, 1))
+    assert torch.equal(s[:, 4:], x[:, 4:])
+    one = O.temporal_shift(x[:1])
+    assert float(one[:, :4].abs().sum()) == 0.0
