@@ -411,6 +411,10 @@ struct bsvd_handle {
   uint16_t *bufH0 = nullptr, *bufH1 = nullptr, *bufX1 = nullptr, *bufQ0 = nullptr, *bufQ1 = nullptr;
   std::vector<StageLaunch> plan;
   int last_launches = 0;
+  // per-stage event timing
+  int profiling = 0;
+  std::vector<std::vector<cudaEvent_t>> ev_sets;   // each: BSVD_NUM_STAGES + 1 events
+  int ev_used = 0;
   // pinned/device staging for the host entry
   float* d_in = nullptr; float* d_nmap = nullptr; float* d_out = nullptr;
   size_t d_in_bytes = 0, d_nmap_bytes = 0, d_out_bytes = 0;
@@ -564,6 +568,8 @@ int bsvd_destroy(bsvd_handle* h) {
   if (!h) return 0;
   free_workspace(h);
   for (auto& s : h->stages) free_stage(s);
+  for (auto& set : h->ev_sets)
+    for (auto& e : set) cudaEventDestroy(e);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_nmap) cudaFree(h->d_nmap);
   if (h->d_out) cudaFree(h->d_out);
@@ -591,6 +597,41 @@ int bsvd_set_weights(bsvd_handle* h, int layer, const float* w, const float* bia
   return upload_stage(sd, w, bias, h->bf16);
 }
 
+int bsvd_set_profiling(bsvd_handle* h, int on) {
+  if (!h) return fail("null handle");
+  h->profiling = on ? 1 : 0;
+  if (on) h->ev_used = 0;
+  return 0;
+}
+
+int bsvd_get_stage_ms(bsvd_handle* h, float* ms, int n, int* passes) {
+  if (!h || !ms || n < BSVD_NUM_STAGES) return fail("bad arguments");
+  for (int i = 0; i < BSVD_NUM_STAGES; ++i) ms[i] = 0.f;
+  for (int s = 0; s < h->ev_used; ++s) {
+    auto& set = h->ev_sets[s];
+    CUDA_TRY(cudaEventSynchronize(set[BSVD_NUM_STAGES]));
+    for (int i = 0; i < BSVD_NUM_STAGES; ++i) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, set[i], set[i + 1]));
+      ms[i] += t;
+    }
+  }
+  if (passes) *passes = h->ev_used;
+  return 0;
+}
+
+int bsvd_stage_info(const bsvd_handle* h, int stage, int* cin, int* cout, int* stride, int* ntile,
+                    int* rows) {
+  if (!h || stage < 1 || stage > BSVD_NUM_LAYERS) return fail("bad stage index %d", stage);
+  const StageSpec& s = h->stages[stage - 1].spec;
+  if (cin) *cin = s.cin;
+  if (cout) *cout = s.cout;
+  if (stride) *stride = s.stride;
+  if (ntile) *ntile = s.ntile;
+  if (rows) *rows = s.rows;
+  return 0;
+}
+
 int bsvd_last_launch_count(const bsvd_handle* h) { return h ? h->last_launches : 0; }
 size_t bsvd_workspace_bytes(const bsvd_handle* h) { return h ? h->ws_bytes : 0; }
 
@@ -602,14 +643,26 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
   if (build_clip_plan(h, in, noise_map, out, T, in_c, H, W)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t>* evs = nullptr;
+  if (h->profiling) {
+    if (h->ev_used == (int)h->ev_sets.size()) {
+      std::vector<cudaEvent_t> set(BSVD_NUM_STAGES + 1);
+      for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
+      h->ev_sets.push_back(set);
+    }
+    evs = &h->ev_sets[h->ev_used++];
+    CUDA_TRY(cudaEventRecord((*evs)[0], st));
+  }
   const long long npix = (long long)T * H * W;
   const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
   if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
   else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
   CUDA_TRY(cudaGetLastError());
+  if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   int launches = 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
     if (launch_stage(h->plan[l], st)) return 1;
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[l + 2], st));
     ++launches;
   }
   h->last_launches = launches;

@@ -102,6 +102,20 @@ int bsvd_last_launch_count(const bsvd_handle* h);
 /* bytes of device workspace currently held */
 size_t bsvd_workspace_bytes(const bsvd_handle* h);
 
+/* Per-stage device timing (CUDA events on the caller's stream, recorded between the stage launches
+ * of bsvd_forward_clip).  on=1 starts a fresh accumulation.  bsvd_get_stage_ms synchronises the
+ * recorded events and writes, for stage 0 (input staging) and stages 1..32 (the 32 conv stages),
+ * the device milliseconds summed over the forwards recorded since profiling was switched on;
+ * returns the number of forwards accumulated through *passes. */
+#define BSVD_NUM_STAGES 33
+int bsvd_set_profiling(bsvd_handle* h, int on);
+int bsvd_get_stage_ms(bsvd_handle* h, float* ms, int n, int* passes);
+/* Static description of stage i (1..32) for roofline arithmetic: kernel instance name,
+ * algorithmic FLOPs and activation bytes per frame-pixel-independent unit are computed by the
+ * caller from (cin, cout, stride, ntile, rows). */
+int bsvd_stage_info(const bsvd_handle* h, int stage, int* cin, int* cout, int* stride, int* ntile,
+                    int* rows);
+
 /* -- single fused conv stage (test / micro-benchmark hook) ------------------------------------
  * Runs ONE fused 3x3 conv stage exactly as the network does (same kernels), on NHWC
  * 16-bit activations.  Used by tests/ to check every kernel variant against the oracle.

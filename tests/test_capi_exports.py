@@ -1,0 +1,109 @@
+"""CPU-side checks of the boundary: the C-ABI library loads here (no GPU) and exports every symbol
+include/bsvd_b200.h declares; the nn.Module mirrors the reference's names and error behaviour."""
+import os
+import re
+
+import pytest
+import torch
+
+from bsvd_b200 import capi
+from oracle import bsvd_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "bsvd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bsvd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    names = _declared()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(capi.EXPORTS) == names
+
+
+def test_version_and_error_string():
+    lib = capi.load_library()
+    assert b"sm_100a" in lib.bsvd_version()
+    assert isinstance(lib.bsvd_last_error(), bytes)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    import ctypes as C
+    lib = capi.load_library()
+    cfg = capi.BsvdConfig()
+    cfg.chns[0], cfg.chns[1], cfg.chns[2] = 64, 128, 256
+    cfg.mid_ch = cfg.interm_ch = 64
+    cfg.in_ch, cfg.out_ch, cfg.act_relu6, cfg.norm_none, cfg.device = 4, 3, 1, 1, -1
+    h = C.c_void_p()
+    assert lib.bsvd_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CPU fallback" in lib.bsvd_last_error()
+
+
+def test_create_rejects_other_configs():
+    import ctypes as C
+    lib = capi.load_library()
+    cfg = capi.BsvdConfig()
+    cfg.chns[0], cfg.chns[1], cfg.chns[2] = 32, 64, 128
+    cfg.mid_ch, cfg.interm_ch = 64, 30
+    cfg.in_ch, cfg.out_ch, cfg.act_relu6, cfg.norm_none, cfg.device = 4, 3, 1, 1, -1
+    h = C.c_void_p()
+    assert lib.bsvd_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"BSVD-64" in lib.bsvd_last_error()
+
+
+def _net(**kw):
+    from bsvd_b200.arch import BSVD
+    args = dict(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+                act='relu6', pretrain_ckpt=None)
+    args.update(kw)
+    return BSVD(**args)
+
+
+def test_module_state_dict_uses_reference_names():
+    net = _net()
+    keys = {k.rsplit(".", 1)[0] for k in net.state_dict()}
+    assert keys == set(O.bsvd_keys())          # names checked against the reference in make_golden.py
+    assert sum(p.numel() for p in net.parameters()) == 9815683
+    assert net.shift_num == 16
+    assert "B200-native" in str(net)
+
+
+def test_module_loads_tsn_checkpoint(tmp_path):
+    sd = O.make_synthetic_params(0)
+    for prefix in ("", "module."):
+        ck = tmp_path / f"ck{len(prefix)}.pth"
+        torch.save({"params": {prefix + k: v for k, v in sd.items()}}, ck)
+        net = _net(pretrain_ckpt=str(ck))
+        got = O.layers_from_bsvd_state(net.state_dict())
+        want = O.layers_from_tsn_state(sd)
+        assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, want))
+
+
+def test_module_state_dict_roundtrip_and_half():
+    a, b = _net(), _net()
+    b.load_state_dict(a.state_dict(), strict=True)
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+    assert next(a.half().parameters()).dtype == torch.float16
+
+
+def test_module_rejects_unsupported_configs():
+    with pytest.raises(NotImplementedError):
+        _net(chns=[32, 64, 128], interm_ch=30)
+    with pytest.raises(NotImplementedError):
+        _net(act='relu')
+    with pytest.raises(NotImplementedError):
+        _net(norm='bn')
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_module_forward_fails_loudly_without_gpu():
+    net = _net()
+    with pytest.raises(Exception):
+        net(torch.zeros(1, 2, 4, 8, 8))

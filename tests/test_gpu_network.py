@@ -1,0 +1,158 @@
+"""Whole hot path on the B200 through the drop-in module / C ABI against (a) the committed
+reference-generated fixtures, (b) the CPU oracle on seeded inputs, (c) size-independent
+properties at the full 540x960 size.
+
+Tolerances are BASELINE.json's: max-abs <= 1e-3 in the default mode (fp16 operands, fp32
+accumulate; the fp32-parity configuration) and <= 1e-2 in bf16 mode, on trained-like weights.  The
+default-init stress fixture saturates ReLU6 (|y| ~ 12): even the reference's own reduced-precision
+run differs from its fp32 by 0.34 there, so it is checked with a relative bound."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bsvd_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+TOL = {"fp16": 1e-3, "bf16": 1e-2}
+
+
+def make_net(seed=0, scale=0.5, prec=None):
+    from bsvd_b200.arch import BSVD
+    sd = O.make_synthetic_params(seed, scale)
+    net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+               act='relu6', pretrain_ckpt=None, precision=prec)
+    net.load_tsn_state(sd)
+    return net.cuda().eval(), O.layers_from_tsn_state(sd)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_matches_reference_fixture(path, prec):
+    g = np.load(path)
+    net, _ = make_net(int(g["param_seed"]), float(g["weight_scale"]), prec)
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    assert O.params_digest({"x": x}) == str(g["x_digest"])
+    with torch.no_grad():
+        y = net(x[None, :, :3].cuda(), noise_map=x[None, :, 3:4].cuda())[0].float().cpu()
+    ref = torch.from_numpy(g["y_stream"])
+    err = float((y - ref).abs().max())
+    if float(g["weight_scale"]) < 1.0:
+        assert err <= TOL[prec], err
+    else:
+        assert err <= (4e-3 if prec == "fp16" else 4e-2) * float(ref.abs().max()), err
+    assert net.last_launch_count == 33
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 96), (2, 136, 264), (3, 36, 260), (12, 16, 16)])
+def test_matches_oracle(shape):
+    T, H, W = shape
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(T, H, W, seed=11)
+    with torch.no_grad():
+        y = net(x[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x)
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+
+
+def test_full_size_540x960_against_oracle_and_psnr():
+    net, layers = make_net()
+    x, clean = O.make_synthetic_clip(2, 540, 960, seed=1)
+    with torch.no_grad():
+        y = net(x[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x)
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+    # PSNR delta (calculate_psnr_float semantics after clamp, validation_seq_infer.py:24-26)
+    for t in range(2):
+        d = abs(O.psnr_float(y[t].clamp(0, 1), clean[t]) - O.psnr_float(ref[t].clamp(0, 1), clean[t]))
+        assert d < 0.01, d
+
+
+def test_deterministic_and_stateless_across_calls():
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(4, 32, 48, seed=3)
+    xc = x[None].cuda()
+    with torch.no_grad():
+        a = net(xc).clone()
+        other, _ = O.make_synthetic_clip(4, 32, 48, seed=4)
+        net(other[None].cuda())
+        b = net(xc)
+    assert torch.equal(a, b)
+
+
+def test_host_entry_is_bit_identical_to_device_entry():
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(3, 40, 72, seed=5)
+    with torch.no_grad():
+        a = net(x[None].cuda())[0].float().cpu()
+    b = net.denoise_host(x.pin_memory())
+    assert torch.equal(a, b)
+    c = net.denoise_host(x[:, :3].contiguous(), x[:, 3:4].contiguous())
+    assert torch.equal(a, c)
+
+
+def test_batch_is_one_stream_like_the_reference_unless_independent():
+    # bsvd_arch.py:494-495: [N,F,...] is reshaped to ONE stream of N*F frames
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(6, 24, 32, seed=6)
+    xc = x.cuda()
+    with torch.no_grad():
+        one = net(xc[None])[0]
+        two = net(xc.reshape(2, 3, 4, 24, 32))
+        assert torch.equal(one, two.reshape(6, 3, 24, 32))
+        net.independent_clips = True
+        sep = net(xc.reshape(2, 3, 4, 24, 32))
+        a = net(xc[None, :3])[0]
+        b = net(xc[None, 3:])[0]
+    assert torch.equal(sep[0], a) and torch.equal(sep[1], b)
+    assert not torch.equal(sep.reshape(6, 3, 24, 32), one)
+
+
+def test_streaming_forward_list_and_tensor():
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(3, 24, 40, seed=7)
+    with torch.no_grad():
+        a = net.streaming_forward(x.cuda())
+        b = net.streaming_forward([x[i:i + 1] for i in range(3)])
+    assert torch.equal(a, b)
+    assert float((a.float().cpu() - O.forward_clip(layers, x)).abs().max()) <= TOL["fp16"]
+
+
+def test_autocast_and_half_weights_like_profile_py():
+    # profile.py:79-83: net.half() under torch.cuda.amp.autocast(True); output dtype = autocast dtype
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(2, 24, 32, seed=8)
+    ref = O.forward_clip(layers, x)
+    net = net.half()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y = net(x[None].cuda())
+    assert y.dtype == torch.float16
+    # weights themselves were rounded to fp16 by .half(): operands identical to the fp32-weights path
+    assert float((y[0].float().cpu() - ref).abs().max()) <= 2e-3
+
+
+def test_rejects_sizes_the_reference_rejects():
+    from bsvd_b200.capi import BsvdError
+    net, _ = make_net()
+    with pytest.raises(BsvdError):
+        net(torch.zeros(1, 2, 4, 18, 32, device="cuda"))     # H % 4 != 0
+    with pytest.raises(BsvdError):
+        net(torch.zeros(1, 2, 5, 16, 32, device="cuda"))     # wrong channel count
+
+
+def test_temporal_linearity_property_full_size():
+    """Size-independent property at the bench size: with zero bias-free shift there is no closed
+    form, but frames far apart in time cannot influence each other beyond the 16-frame receptive
+    field: changing frame 0 of a 40-frame stream must leave frames >= 17 bit-identical."""
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(20, 64, 64, seed=9)
+    x2 = x.clone()
+    x2[0, :3] += 0.25
+    with torch.no_grad():
+        a = net(x[None].cuda())[0]
+        b = net(x2[None].cuda())[0]
+    assert torch.equal(a[17:], b[17:])
+    assert not torch.equal(a[:8], b[:8])
