@@ -212,19 +212,28 @@ struct StageIO {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// dynamic shared memory: 227 KB opt-in limit minus the kernel's static shared (barriers, bias)
+constexpr size_t kSmemOptIn = 232448 - 3072;
+constexpr size_t kStagingBytes = 8 * kStageBytesPerWarp;   // epilogue staging of the 8 epilogue warps
 
+template <int NTILE, int R, bool BF16>
+static int launch_inst(const CUtensorMap& map, const ConvParams& p, int grid, size_t smem,
+                       cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE, R, BF16>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+    attr_done = true;
+  }
+  conv3x3_tc_kernel<NTILE, R, BF16><<<grid, kThreads, smem, st>>>(map, p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 template <int NTILE, int R>
 static int launch_one(const CUtensorMap& map, const ConvParams& p, int grid, size_t smem,
                       cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE, R>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    attr_done = true;
-  }
-  conv3x3_tc_kernel<NTILE, R><<<grid, kThreads, smem, st>>>(map, p);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
+  return (p.flags & EPI_BF16) ? launch_inst<NTILE, R, true>(map, p, grid, smem, st)
+                              : launch_inst<NTILE, R, false>(map, p, grid, smem, st);
 }
 
 struct StageLaunch {
@@ -264,7 +273,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.mode = (s.stride == 2) ? 1 : 0;
   p.cin_total = s.cin;
   p.w_stage_bytes = (uint32_t)s.ntile * 128u;
-  const size_t budget = 232448 - 2048;   // dynamic smem opt-in limit minus alignment slack/static
+  const size_t budget = kSmemOptIn - 1024 - kStagingBytes;   // minus alignment slack and staging
   if (p.mode == 0) {
     p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
     p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
@@ -315,7 +324,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
                          : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
   if (rc) return rc;
   L->grid = std::min(p.total_tiles, num_sms());
-  L->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes;
+  L->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
+            kStagingBytes;
   L->ntile = s.ntile; L->rows = s.rows;
   return 0;
 }

@@ -17,9 +17,11 @@
 // space-to-depth view of the same NHWC tensor.  Weights are pre-swizzled on the host and
 // streamed with 1-D bulk copies (or kept resident when the whole filter bank fits).
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0      TMA producer          warp 1      MMA issuer + TMEM allocator
-//   warps 2..5  epilogue (TMEM -> registers -> bias/act/skip/residual -> 128-bit global stores)
+//   warps 2..9  epilogue: TMEM -> registers -> bias/act/skip/residual in fp32 -> 16-bit ->
+//               per-warp swizzled smem staging -> coalesced 128-bit global stores (the
+//               bidirectional-buffer fold routing and PixelShuffle scatter happen at the store)
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
 #pragma once
 #include <cuda.h>
@@ -34,7 +36,10 @@ constexpr int kChunk = 64;         // channels per K chunk (128 B of 16-bit)
 constexpr int kHaloPx = kRunPx + 2;
 constexpr int kRowBytes = kHaloPx * 128;   // one haloed image row of one chunk: 16640 B
 constexpr int kMaxStages = 12;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kStageBytesPerWarp = 2048;   // epilogue staging: [32 px][32 ch] 16-bit per warp
+constexpr int kMaxBias = 512;
 
 enum : int {
   EPI_RELU6 = 1,
@@ -245,78 +250,7 @@ __device__ __forceinline__ float load16(const void* p, long long idx) {
 }
 
 // --------------------------------------------------------------------------------------------
-// Epilogue for one group of 8 consecutive GEMM columns of one pixel.
-// --------------------------------------------------------------------------------------------
-template <bool BF16>
-__device__ __forceinline__ void epilogue_vec8(const ConvParams& p, float (&f)[8], int n0, int t,
-                                              int y, int x) {
-  const int flags = p.flags;
-  int c0 = n0, oy = y, ox = x;
-  if (flags & EPI_PIXSHUF) {
-    // GEMM columns are ordered (subpixel q = 2i+j, channel c): conv channel c*4+q -> out[c, 2y+i, 2x+j]
-    const int q = n0 / p.out_C;
-    c0 = n0 - q * p.out_C;
-    oy = 2 * y + (q >> 1);
-    ox = 2 * x + (q & 1);
-  }
-  const long long pix = static_cast<long long>(oy) * p.out_W + ox;
-  if (flags & EPI_SKIP) {
-    const uint4 s = *reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(p.skip) + t * p.skip_frame_stride + pix * p.skip_C + c0);
-    float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
-           d = unpack2<BF16>(s.w);
-    f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
-    f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
-  }
-  if (flags & EPI_RELU6) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = relu6f(f[i]);
-  }
-  if ((flags & EPI_RESID_IN) && n0 == 0) {
-    const long long plane = static_cast<long long>(p.H) * p.W;
-    const float* r = p.resid_in + (static_cast<long long>(t) * p.resid_C) * plane +
-                     static_cast<long long>(y) * p.W + x;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
-  }
-  uint4 v;
-  v.x = pack2<BF16>(f[0], f[1]);
-  v.y = pack2<BF16>(f[2], f[3]);
-  v.z = pack2<BF16>(f[4], f[5]);
-  v.w = pack2<BF16>(f[6], f[7]);
-  const long long off = pix * p.out_C + c0;
-  uint16_t* base = reinterpret_cast<uint16_t*>(p.out);
-  if (!(flags & EPI_SHIFT)) {
-    *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = v;
-    return;
-  }
-  // Bidirectional-buffer shift folded into the store (ShiftConv.forward, bsvd_arch.py:42-50):
-  // the consumer conv of frame u reads channels [0,f) of frame u+1 and [f,2f) of frame u-1, so the
-  // producer of frame t writes those folds straight into the tensors of frames t-1 / t+1.
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  if (c0 < p.fold) {
-    if (p.ring_mode) {
-      if (p.out_prev) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_prev) + off) = v;
-      if (flags & EPI_ZERO_FUTURE) *reinterpret_cast<uint4*>(base + off) = zero;
-    } else {
-      if (t > 0) *reinterpret_cast<uint4*>(base + (t - 1) * p.out_frame_stride + off) = v;
-      if (t == p.T - 1) *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = zero;
-    }
-  } else if (c0 < 2 * p.fold) {
-    if (p.ring_mode) {
-      if (p.out_next) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_next) + off) = v;
-      if (!p.out_prev) *reinterpret_cast<uint4*>(base + off) = zero;   // first frame of a stream
-    } else {
-      if (t + 1 < p.T) *reinterpret_cast<uint4*>(base + (t + 1) * p.out_frame_stride + off) = v;
-      if (t == 0) *reinterpret_cast<uint4*>(base + off) = zero;
-    }
-  } else {
-    *reinterpret_cast<uint4*>(base + t * p.out_frame_stride + off) = v;
-  }
-}
-
-// --------------------------------------------------------------------------------------------
-// The kernel
+// tile bookkeeping
 // --------------------------------------------------------------------------------------------
 struct TileCoord {
   int nt, t, y0, x0;
@@ -335,7 +269,129 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
   return c;
 }
 
-template <int NTILE, int R>
+// --------------------------------------------------------------------------------------------
+// Epilogue of one unit = 32 GEMM columns x 32 pixels of one warp.
+//   phase 1 (lane = pixel): fp32 bias / skip add / ReLU6 / residual, round to 16 bit, park the
+//            pixel's 64 bytes in the warp's staging tile (XOR-swizzled: conflict-free both ways)
+//   phase 2 (lane = 16-byte chunk): read back transposed so that 4 lanes cover one pixel's 64
+//            contiguous bytes, route to the destination frame/sub-pixel and store.
+// --------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoord& tc, int y,
+                                              int nbase, const uint32_t (&v)[32],
+                                              const float* bias_s, uint32_t stg, int quad,
+                                              int lane) {
+  const int flags = p.flags;
+  // ------------------------------ phase 1 ------------------------------
+  {
+    const int x = tc.x0 + quad * 32 + lane;
+    const bool valid = (x < p.W) && (y < p.H);
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+      f[0] = __uint_as_float(v[8 * j + 0]) + ba.x; f[1] = __uint_as_float(v[8 * j + 1]) + ba.y;
+      f[2] = __uint_as_float(v[8 * j + 2]) + ba.z; f[3] = __uint_as_float(v[8 * j + 3]) + ba.w;
+      f[4] = __uint_as_float(v[8 * j + 4]) + bb.x; f[5] = __uint_as_float(v[8 * j + 5]) + bb.y;
+      f[6] = __uint_as_float(v[8 * j + 6]) + bb.z; f[7] = __uint_as_float(v[8 * j + 7]) + bb.w;
+      if ((flags & EPI_SKIP) && valid) {
+        const int n0 = nbase + 8 * j;
+        int c0 = n0, oy = y, ox = x;
+        if (flags & EPI_PIXSHUF) {
+          const int q = n0 / p.out_C;
+          c0 = n0 - q * p.out_C;
+          oy = 2 * y + (q >> 1);
+          ox = 2 * x + (q & 1);
+        }
+        const uint4 s = __ldg(reinterpret_cast<const uint4*>(
+            reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
+            (static_cast<long long>(oy) * p.out_W + ox) * p.skip_C + c0));
+        const float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
+                     d = unpack2<BF16>(s.w);
+        f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+        f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
+      }
+      if (flags & EPI_RELU6) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = relu6f(f[i]);
+      }
+      if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid) {
+        // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
+        const long long plane = static_cast<long long>(p.H) * p.W;
+        const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
+                         static_cast<long long>(y) * p.W + x;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+      }
+      uint4 o;
+      o.x = pack2<BF16>(f[0], f[1]); o.y = pack2<BF16>(f[2], f[3]);
+      o.z = pack2<BF16>(f[4], f[5]); o.w = pack2<BF16>(f[6], f[7]);
+      const uint32_t a = stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
+                   "r"(o.z), "r"(o.w) : "memory");
+    }
+  }
+  __syncwarp();
+  // ------------------------------ phase 2 ------------------------------
+  {
+    const int j = lane & 3;
+    const int n0 = nbase + 8 * j;
+    int c0 = n0, q = 0;
+    if (flags & EPI_PIXSHUF) {
+      q = n0 / p.out_C;
+      c0 = n0 - q * p.out_C;
+    }
+    // fold routing of this 8-channel group (ShiftConv.forward, bsvd_arch.py:42-50): the consumer
+    // conv of frame u reads channels [0,f) of frame u+1 and [f,2f) of frame u-1, so the producer
+    // of frame t stores those folds straight into the tensors of frames t-1 / t+1.
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + tc.t * p.out_frame_stride;
+    uint16_t* zdst = nullptr;       // own-frame location that must read as zero (clip ends)
+    if (flags & EPI_SHIFT) {
+      uint16_t* own = dst;
+      if (c0 < p.fold) {
+        if (p.ring_mode) {
+          dst = reinterpret_cast<uint16_t*>(p.out_prev);
+          if (flags & EPI_ZERO_FUTURE) zdst = own;
+        } else {
+          dst = (tc.t > 0) ? own - p.out_frame_stride : nullptr;
+          if (tc.t == p.T - 1) zdst = own;
+        }
+      } else if (c0 < 2 * p.fold) {
+        if (p.ring_mode) {
+          dst = reinterpret_cast<uint16_t*>(p.out_next);
+          if (!p.out_prev) zdst = own;
+        } else {
+          dst = (tc.t + 1 < p.T) ? own + p.out_frame_stride : nullptr;
+          if (tc.t == 0) zdst = own;
+        }
+      }
+    }
+    const int oy = (flags & EPI_PIXSHUF) ? 2 * y + (q >> 1) : y;
+    const long long rowoff = static_cast<long long>(oy) * p.out_W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pl = 8 * i + (lane >> 2);
+      const uint32_t a = stg + pl * 64 + ((j ^ ((pl >> 1) & 3)) << 4);
+      uint4 o;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(a) : "memory");
+      const int x = tc.x0 + quad * 32 + pl;
+      if (x < p.W && y < p.H) {
+        const int ox = (flags & EPI_PIXSHUF) ? 2 * x + (q & 1) : x;
+        const long long off = (rowoff + ox) * p.out_C + c0;
+        if (dst) *reinterpret_cast<uint4*>(dst + off) = o;
+        if (zdst) *reinterpret_cast<uint4*>(zdst + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// --------------------------------------------------------------------------------------------
+// The kernel
+// --------------------------------------------------------------------------------------------
+template <int NTILE, int R, bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 16 || NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
@@ -345,6 +401,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
+  __shared__ __align__(16) float bias_s[kMaxBias];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -354,6 +411,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + p.a_stages * p.a_stage_bytes;
+  const uint32_t stg_base = w_base + p.w_stages * p.w_stage_bytes;
 
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
@@ -372,10 +430,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 128);
+      mbar_init(acc_empty(b), kEpiThreads);
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < p.n_tiles * NTILE; i += kThreads) bias_s[i] = p.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
@@ -433,7 +492,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(NTILE, (p.flags & EPI_BF16) ? 1 : 0);
+      const uint32_t idesc = make_idesc(NTILE, BF16 ? 1 : 0);
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -468,12 +527,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, acc);
               }
             }
-            if (p.w_resident) {
-              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
-            } else {
-              umma_commit(w_empty(sw));
-              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
-            }
+            if (!p.w_resident) umma_commit(w_empty(sw));
+            if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
             if (p.mode == 1) {
               umma_commit(a_empty(sa));
               if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
@@ -489,59 +544,75 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ======================================= epilogue =======================================
+    const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;          // pixel offset inside the 128-px run
-    const bool bf16 = (p.flags & EPI_BF16) != 0;
+    const int half = ew >> 2;                  // two warps share a quadrant and split the units
+    const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile);
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
-      const int x = tc.x0 + row;
-#pragma unroll 1
-      for (int r = 0; r < R; ++r) {
-        const int y = tc.y0 + r;
-        const bool valid = (x < p.W) && (y < p.H);
-        constexpr int LDW = (NTILE >= 32) ? 32 : 16;
-#pragma unroll 1
-        for (int g = 0; g < NTILE / LDW; ++g) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                 buf * kAccCols + r * NTILE + g * LDW;
-          if constexpr (LDW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+      const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
+      if constexpr (NTILE == 16) {
+        // temp2 outc.3 + residual (bsvd_arch.py:394, 408-414): fp32 NCHW out = temp1_out[:, :3] - conv[:, :3]
+        const int r = half;                    // R == 2: one row per warp half
+        uint32_t v[32];
+        tmem_ld16(tacc + r * NTILE, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(acc_empty(buf));
+        const int x = tc.x0 + quad * 32 + lane, y = tc.y0 + r;
+        if (x < p.W && y < p.H) {
+          const long long plane = static_cast<long long>(p.H) * p.W;
+          const long long pix = static_cast<long long>(y) * p.W + x;
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane + pix;
+          const uint2 s = __ldg(reinterpret_cast<const uint2*>(
+              reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride + pix * p.skip_C));
+          const float2 s01 = unpack2<BF16>(s.x), s23 = unpack2<BF16>(s.y);
+          o[0] = s01.x - (__uint_as_float(v[0]) + bias_s[0]);
+          o[plane] = s01.y - (__uint_as_float(v[1]) + bias_s[1]);
+          o[2 * plane] = s23.x - (__uint_as_float(v[2]) + bias_s[2]);
+        }
+      } else {
+        constexpr int G = NTILE / 32;          // 32-column groups per row
+        constexpr int kUnits = R * G;
+        constexpr int kMine = kUnits / 2;
+        static_assert(kUnits % 2 == 0, "units must split evenly over the two warp halves");
+        const int u0 = half * kMine;
+        const int nb0 = tc.nt * NTILE;         // global GEMM column of this tile's first column
+        uint32_t va[32], vb[32];
+        tmem_ld32(tacc + (u0 / G) * NTILE + (u0 % G) * 32, va);
+#pragma unroll
+        for (int k = 0; k < kMine; k += 2) {
           tmem_ld_wait();
-          if (valid) {
-            const int nbase = tc.nt * NTILE + g * LDW;
-            if (p.flags & EPI_FINAL) {
-              // temp2 outc.3 + residual (bsvd_arch.py:394, 408-414): out = temp1_out[:, :3] - conv[:, :3]
-              if (g == 0) {
-                const long long plane = static_cast<long long>(p.H) * p.W;
-                const long long pix = static_cast<long long>(y) * p.W + x;
-                float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane + pix;
-                const long long sidx = tc.t * p.skip_frame_stride + pix * p.skip_C;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  const float s = bf16 ? load16<true>(p.skip, sidx + i) : load16<false>(p.skip, sidx + i);
-                  o[i * plane] = s - (__uint_as_float(v[i]) + __ldg(p.bias + i));
-                }
-              }
+          if (k + 1 < kMine) {
+            const int u = u0 + k + 1;
+            tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
+          } else {
+            tc_fence_before();
+            mbar_arrive(acc_empty(buf));       // accumulator drained: MMA may reuse the buffer
+          }
+          {
+            const int u = u0 + k;
+            epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, bias_s, stg, quad, lane);
+          }
+          if (k + 1 < kMine) {
+            tmem_ld_wait();
+            if (k + 2 < kMine) {
+              const int u = u0 + k + 2;
+              tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
             } else {
-#pragma unroll
-              for (int j = 0; j < LDW / 8; ++j) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  f[i] = __uint_as_float(v[j * 8 + i]) + __ldg(p.bias + nbase + j * 8 + i);
-                if (bf16) epilogue_vec8<true>(p, f, nbase + j * 8, tc.t, y, x);
-                else epilogue_vec8<false>(p, f, nbase + j * 8, tc.t, y, x);
-              }
+              tc_fence_before();
+              mbar_arrive(acc_empty(buf));
             }
+            const int u = u0 + k + 1;
+            epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, bias_s, stg, quad, lane);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty(buf));
     }
   }
 
