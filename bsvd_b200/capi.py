@@ -23,7 +23,7 @@ EXPORTS = (
     "bsvd_create", "bsvd_destroy", "bsvd_last_error", "bsvd_version", "bsvd_set_weights",
     "bsvd_layer_shape", "bsvd_forward_clip", "bsvd_forward_clip_host", "bsvd_stream_push",
     "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
-    "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info",
+    "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info", "bsvd_last_stage_ms",
 )
 NUM_STAGES = 33
 
@@ -75,6 +75,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_set_profiling.argtypes = [vp, ci]
     lib.bsvd_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float), ci, cip]
     lib.bsvd_stage_info.argtypes = [vp, ci, cip, cip, cip, cip, cip]
+    lib.bsvd_last_stage_ms.restype = C.c_float
     lib.bsvd_conv_stage.argtypes = [C.POINTER(BsvdConvDesc), vp, vp, vp, vp, vp, vp]
     if path is None:
         _lib = lib

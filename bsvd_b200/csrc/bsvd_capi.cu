@@ -721,6 +721,8 @@ int bsvd_reset(bsvd_handle* h) {
 }
 
 // ---- single-stage hook -------------------------------------------------------------------------
+static float g_last_stage_ms = 0.f;
+float bsvd_last_stage_ms(void) { return g_last_stage_ms; }
 int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, const float* bias,
                     const void* skip, void* out, void* stream) {
   if (!d || !in || !w || !out) return fail("null argument");
@@ -745,9 +747,26 @@ int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, con
   const int Co = s.pixshuf ? s.cout / 4 : s.cout;
   io.skip = skip; io.skip_C = Co; io.skip_frame_stride = (long long)Ho * Wo * Co;
   StageLaunch L;
-  int rc = plan_stage(sd, io, bf16, d->debug_variant, &L);
-  if (!rc) rc = launch_stage(L, reinterpret_cast<cudaStream_t>(stream));
-  cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  int rc = plan_stage(sd, io, bf16, d->debug_variant & 0xff, &L);
+  const int a_over = (d->debug_variant >> 8) & 0xf;
+  if (!rc && a_over) {   // debug: override the number of A stages (smem permitting)
+    L.smem += (size_t)(a_over - L.p.a_stages) * L.p.a_stage_bytes;
+    L.p.a_stages = a_over;
+    if (L.smem > kSmemOptIn) rc = fail("debug a_stages override exceeds shared memory");
+  }
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = ((d->debug_variant >> 12) & 0xf) + 1;
+  if (!rc) rc = launch_stage(L, cst);                 // warm-up / the result
+  cudaEventRecord(e0, cst);
+  for (int i = 0; i < reps && !rc; ++i) rc = launch_stage(L, cst);
+  cudaEventRecord(e1, cst);
+  cudaError_t e = cudaStreamSynchronize(cst);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  g_last_stage_ms = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   free_stage(sd);
   if (!rc && e != cudaSuccess) return fail("conv stage failed: %s", cudaGetErrorString(e));
   return rc;

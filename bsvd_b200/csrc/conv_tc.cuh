@@ -67,7 +67,8 @@ struct ConvParams {
   uint32_t a_stage_bytes, w_stage_bytes;   // stage strides in smem (multiples of 1024)
   uint32_t a_tx_bytes;                     // bytes one A-stage TMA box delivers
   int w_resident;
-  int desc_variant;     // 0 production; 1 = base_offset from address (experiment)
+  int desc_variant;     // 0 production; debug bits: 2 skip MMA issue, 4 skip epilogue stores,
+                        // 8 tap offsets forced to 0 (aligned A), 16 no TMA loads at all
   // ---- operands ----
   const void* wpack;    // [n_tile][chunk][tap][NTILE][64] 16-bit, rows pre-swizzled (SW128)
   const float* bias;    // [GEMM N]
@@ -200,6 +201,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -450,7 +460,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (lane == 0 && !(p.desc_variant & 16)) {
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       bool first = true;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -491,56 +501,70 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(NTILE, BF16 ? 1 : 0);
-      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(acc_empty(buf), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-        for (int c = 0; c < p.cin_chunks; ++c) {
-          if (p.mode == 0) {
-            mbar_wait(a_full(sa), pa);
-            tc_fence_after();
-          }
-          for (int tap = p.tap_begin; tap < p.tap_end; ++tap) {
-            if (p.mode == 1) {
-              mbar_wait(a_full(sa), pa);
-            }
-            if (!p.w_resident || it == 0) mbar_wait(w_full(sw), pw);
-            tc_fence_after();
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
-            const uint32_t w_stage = w_base + sw * p.w_stage_bytes;
+    // The whole warp walks the (uniform) tile/chunk/tap loops and waits on the barriers; one
+    // elected lane issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are built
+    // once; per MMA only the 32-bit start-address word changes by a compile-time constant.
+    const uint32_t idesc = make_idesc(NTILE, BF16 ? 1 : 0);
+    const uint32_t leader = elect_one();
+    constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);  // SW128, version 1, SBO 1024
+    const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
+    const bool skip_mma = (p.desc_variant & 2) != 0;
+    const bool no_load = (p.desc_variant & 16) != 0;
+    uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(acc_empty(buf), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+      for (int c = 0; c < p.cin_chunks; ++c) {
+        if (p.mode == 0 && !no_load) {
+          mbar_wait(a_full(sa), pa);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (tap < p.tap_begin || tap >= p.tap_end) continue;
+          if (p.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
+          if ((!p.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
+          tc_fence_after();
+          const int dy = tap / 3, dx = tap % 3;
+          // start-address words (>>4) of this stage; LBO field = 1 (unused for SW128 K-major)
+          const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t b_lo0 = (((w_base + sw * p.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t first = (c == 0 && tap == p.tap_begin) ? 0u : 1u;
+          if (leader && !skip_mma) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              const uint32_t a_row = (p.mode == 0)
-                  ? a_stage + static_cast<uint32_t>((r + dy) * kHaloPx + dx) * 128u
-                  : a_stage + static_cast<uint32_t>(r) * (kRunPx * 128u);
+              const uint32_t a_off = (p.mode == 0 && !(p.desc_variant & 8))
+                  ? static_cast<uint32_t>(((r + dy) * kHaloPx + dx) * 8)
+                  : static_cast<uint32_t>(r * (kRunPx * 8));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = make_kmajor_sw128_desc(a_row + k * 32u, p.desc_variant);
-                const uint64_t bd = make_kmajor_sw128_desc(w_stage + k * 32u, 0);
-                const uint32_t acc = (c > 0 || tap > p.tap_begin || k > 0) ? 1u : 0u;
-                umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, acc);
+                const uint64_t ad = desc_hi | (a_lo0 + a_off + k * 2u);
+                const uint64_t bd = desc_hi | (b_lo0 + k * 2u);
+                umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, (k > 0) ? 1u : first);
               }
             }
-            if (!p.w_resident) umma_commit(w_empty(sw));
-            if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
-            if (p.mode == 1) {
-              umma_commit(a_empty(sa));
-              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
-            }
           }
-          if (p.mode == 0) {
-            umma_commit(a_empty(sa));
+          if (leader) {
+            if (!p.w_resident) umma_commit(w_empty(sw));
+            if (p.mode == 1) umma_commit(a_empty(sa));
+          }
+          __syncwarp();
+          if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+          if (p.mode == 1) {
             if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(acc_full(buf));
+        if (p.mode == 0) {
+          if (leader) umma_commit(a_empty(sa));
+          __syncwarp();
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+        }
       }
+      if (leader) umma_commit(acc_full(buf));
+      __syncwarp();
     }
   } else {
     // ======================================= epilogue =======================================
@@ -595,7 +619,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tc_fence_before();
             mbar_arrive(acc_empty(buf));       // accumulator drained: MMA may reuse the buffer
           }
-          {
+          if (!(p.desc_variant & 4)) {
             const int u = u0 + k;
             epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, bias_s, stg, quad, lane);
           }
@@ -609,7 +633,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               mbar_arrive(acc_empty(buf));
             }
             const int u = u0 + k + 1;
-            epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, bias_s, stg, quad, lane);
+            if (!(p.desc_variant & 4))
+              epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, bias_s, stg, quad, lane);
           }
         }
       }

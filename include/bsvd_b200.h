@@ -142,6 +142,8 @@ typedef struct bsvd_conv_desc {
  *   f = channels/8. */
 int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w_oihw,
                     const float* bias, const void* skip, void* out, void* stream);
+/* device milliseconds of the (re-)launches timed inside the last bsvd_conv_stage call */
+float bsvd_last_stage_ms(void);
 
 #ifdef __cplusplus
 }
