@@ -408,6 +408,23 @@ using namespace bsvd;
 // ================================================================================================
 // network handle
 // ================================================================================================
+// Streaming ring buffers of one DenBlock (sizes in frames; the reference keeps the same state in
+// BiBufferConv.left/center (bsvd_arch.py:72-74,112-113) and the MemSkip FIFOs (:308-322)):
+//   shifted tensors feeding a BiBufferConv live in 3-slot rings (frames f-1, f, f+1),
+//   skip2 (x0) and skip1 (block input) wait 8 steps -> 9 slots, skip3 (x1) waits 4 steps -> 5 slots.
+enum { kRingP = 0, kRingA, kRingX0, kRingB2, kRingB3, kRingX1, kRingB5, kRingB6, kRingB7, kRingB8,
+       kRingB9, kRingB10, kRingB11, kRingB12, kRingB13, kRingB14, kRingM, kNumRings };
+static const int kRingSlots[kNumRings] = {1, 1, 9, 3, 3, 5, 3, 3, 3, 3, 1, 3, 3, 1, 1, 1, 9};
+static const int kRingRes[kNumRings] = {1, 1, 1, 2, 2, 2, 4, 4, 4, 4, 4, 2, 2, 2, 1, 1, 1};  // 1 full, 2 half, 4 quarter
+// per layer: delay (steps) inside a DenBlock, input ring, output ring
+static const int kLayerDelay[16] = {0, 0, 0, 1, 2, 2, 3, 4, 5, 6, 6, 7, 8, 8, 8, 8};
+static const int kLayerIn[16] = {kRingP, kRingA, kRingX0, kRingB2, kRingB3, kRingX1, kRingB5, kRingB6,
+                                 kRingB7, kRingB8, kRingB9, kRingB10, kRingB11, kRingB12, kRingB13,
+                                 kRingB14};
+static const int kLayerOut[16] = {kRingA, kRingX0, kRingB2, kRingB3, kRingX1, kRingB5, kRingB6, kRingB7,
+                                  kRingB8, kRingB9, kRingB10, kRingB11, kRingB12, kRingB13, kRingB14,
+                                  kRingM};
+static const int kBlockDelay = 8;   // latency of one DenBlock in steps (8 BiBufferConv each)
 struct bsvd_handle {
   bsvd_config cfg;
   int bf16 = 0;
@@ -428,17 +445,32 @@ struct bsvd_handle {
   // pinned/device staging for the host entry
   float* d_in = nullptr; float* d_nmap = nullptr; float* d_out = nullptr;
   size_t d_in_bytes = 0, d_nmap_bytes = 0, d_out_bytes = 0;
+  // ---- streaming mode (feedin_one_element) ----
+  struct StreamLayer {
+    StageLaunch tmpl;                 // planned for T=1 on ring slot 0
+    std::vector<CUtensorMap> maps;    // one per input ring slot
+  };
+  struct Stream {
+    int H = 0, W = 0;
+    long long step = 0;               // pushes so far in this stream
+    long long n_in = 0;               // real frames fed
+    bool ended = false;               // a NULL frame has been pushed
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // rings[blk][k] : device base of ring k of DenBlock blk; see kRing* below
+    uint8_t* ring[2][kNumRings] = {};
+    float* raw = nullptr;             // fp32 [9][4][H][W] ring of the raw network input
+    StreamLayer layers[BSVD_NUM_LAYERS];
+  } stream;
 };
 
 static void build_specs(bsvd_handle* h) {
   // DenBlock (bsvd_arch.py:325-396), BSVD-64: chns 64/128/256; temp1 4->64, temp2 64->3.
   for (int blk = 0; blk < 2; ++blk) {
-    StageSpec* s = nullptr;
     auto S = [&](int l) -> StageSpec& { return h->stages[blk * 16 + l].spec; };
     const int c0 = h->cfg.chns[0], c1 = h->cfg.chns[1], c2 = h->cfg.chns[2];
     const int in_ch = blk == 0 ? h->cfg.in_ch : h->cfg.mid_ch;
     const int out_ch = blk == 0 ? h->cfg.mid_ch : h->cfg.out_ch;
-    (void)s;
     S(0) = StageSpec(); S(0).cin = in_ch; S(0).cout = h->cfg.interm_ch; S(0).relu6 = true;
     S(0).first_im2col = (blk == 0);
     S(1) = StageSpec(); S(1).cin = h->cfg.interm_ch; S(1).cout = c0; S(1).relu6 = true;
@@ -461,6 +493,7 @@ static void build_specs(bsvd_handle* h) {
   }
 }
 
+extern "C" { static void free_stream(bsvd_handle* h); }
 static void free_workspace(bsvd_handle* h) {
   if (h->ws) cudaFree(h->ws);
   h->ws = nullptr; h->ws_bytes = 0; h->plan.clear();
@@ -577,6 +610,7 @@ int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
 int bsvd_destroy(bsvd_handle* h) {
   if (!h) return 0;
   free_workspace(h);
+  free_stream(h);
   for (auto& s : h->stages) free_stage(s);
   for (auto& set : h->ev_sets)
     for (auto& e : set) cudaEventDestroy(e);
@@ -708,15 +742,143 @@ int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nm
   return 0;
 }
 
+static void free_stream(bsvd_handle* h) {
+  auto& S = h->stream;
+  if (S.ws) cudaFree(S.ws);
+  S = bsvd_handle::Stream();
+}
+
+static size_t ring_slot_bytes(int ring, int H, int W) {
+  const int r = kRingRes[ring];
+  const int C = (r == 1) ? 64 : (r == 2 ? 128 : 256);
+  return align_up((size_t)(H / r) * (W / r) * C * 2, 1024);
+}
+
+// Allocate the rings and pre-encode one tensor map per (layer, input ring slot).
+static int build_stream(bsvd_handle* h, int H, int W) {
+  auto& S = h->stream;
+  free_stream(h);
+  S.H = H; S.W = W;
+  size_t total = 0;
+  for (int b = 0; b < 2; ++b)
+    for (int k = 0; k < kNumRings; ++k) total += ring_slot_bytes(k, H, W) * kRingSlots[k];
+  const size_t raw_bytes = align_up((size_t)9 * 4 * H * W * sizeof(float), 1024);
+  total += raw_bytes;
+  CUDA_TRY(cudaMalloc(&S.ws, total));
+  S.ws_bytes = total;
+  uint8_t* p = reinterpret_cast<uint8_t*>(S.ws);
+  S.raw = reinterpret_cast<float*>(p); p += raw_bytes;
+  for (int b = 0; b < 2; ++b)
+    for (int k = 0; k < kNumRings; ++k) { S.ring[b][k] = p; p += ring_slot_bytes(k, H, W) * kRingSlots[k]; }
+  for (int b = 0; b < 2; ++b)
+    for (int l = 0; l < 16; ++l) {
+      auto& SL = S.layers[b * 16 + l];
+      const StageDev& sd = h->stages[b * 16 + l];
+      // block 1 reads the previous block's output ring as its input
+      const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
+      const int in_blk = (b == 1 && l == 0) ? 0 : b;
+      const int r = kRingRes[in_ring];
+      const size_t in_bytes = ring_slot_bytes(in_ring, H, W);
+      StageIO io;
+      io.T = 1; io.H = H / r; io.W = W / r;
+      io.in = S.ring[in_blk][in_ring];
+      io.out = S.ring[b][kLayerOut[l]];          // patched per step
+      io.ring_mode = sd.spec.shift ? 1 : 0;
+      io.zero_future = sd.spec.shift ? 1 : 0;
+      io.out_next = io.out;                      // placeholders so plan_stage's checks pass
+      io.skip = S.ring[b][kRingX0]; io.skip_C = 64;
+      io.resid_in = S.raw; io.resid_C = 4;
+      if (l == 10) { io.skip = S.ring[b][kRingX1]; io.skip_C = 128; }
+      if (l == 15 && b == 1) { io.skip = S.ring[0][kRingM]; io.skip_C = 64; }
+      if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
+      const int nslots = kRingSlots[in_ring];
+      SL.maps.resize(nslots);
+      const int cin_map = sd.spec.first_im2col ? kChunk : sd.spec.cin;
+      for (int k = 0; k < nslots; ++k) {
+        const void* base = S.ring[in_blk][in_ring] + (size_t)k * in_bytes;
+        int rc = (sd.spec.stride == 2) ? make_map_s2(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows)
+                                       : make_map_halo(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows);
+        if (rc) return rc;
+      }
+    }
+  return 0;
+}
+
 int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map, float* out,
                      int in_c, int H, int W, int* produced, void* stream) {
-  (void)h; (void)frame; (void)noise_map; (void)out; (void)in_c; (void)H; (void)W; (void)stream;
   if (produced) *produced = 0;
-  return fail("bsvd_stream_push: streaming schedule not built yet");
+  if (!h || !out) return fail("null argument");
+  if (check_hw(1, frame ? in_c : 4, H, W, frame ? noise_map != nullptr : false)) return 1;
+  for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
+    if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
+  auto& S = h->stream;
+  if (!S.ws || S.H != H || S.W != W) {
+    if (S.ws && S.step != 0) return fail("frame size changed mid-stream (call bsvd_reset first)");
+    if (build_stream(h, H, W)) return 1;
+  }
+  if (frame && S.ended)
+    return fail("a frame was pushed after the end-of-stream marker (call bsvd_reset first)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long s = S.step;
+  const size_t plane = (size_t)H * W;
+  int launches = 0;
+  if (frame) {
+    // keep the raw frame for the temp1 residual 8 steps later (skip1, bsvd_arch.py:380,394)
+    float* slot = S.raw + (size_t)(s % 9) * 4 * plane;
+    CUDA_TRY(cudaMemcpyAsync(slot, frame, plane * in_c * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (noise_map)
+      CUDA_TRY(cudaMemcpyAsync(slot + 3 * plane, noise_map, plane * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    const long long npix = (long long)plane;
+    const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
+    uint16_t* P = reinterpret_cast<uint16_t*>(S.ring[0][kRingP]);
+    if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);
+    else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+    ++S.n_in;
+  } else {
+    S.ended = true;
+  }
+  const long long F = S.n_in;          // frames known so far; final once ended
+  for (int b = 0; b < 2; ++b)
+    for (int l = 0; l < 16; ++l) {
+      const long long f = s - (kLayerDelay[l] + b * kBlockDelay);
+      if (f < 0 || f >= F) continue;   // None propagation (bsvd_arch.py:135,139,219-224,...)
+      auto& SL = S.layers[b * 16 + l];
+      StageLaunch L = SL.tmpl;
+      const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
+      L.map = SL.maps[f % kRingSlots[in_ring]];
+      const int oring = kLayerOut[l];
+      const size_t ob = ring_slot_bytes(oring, H, W);
+      auto oslot = [&](long long ff) { return S.ring[b][oring] + (size_t)(ff % kRingSlots[oring]) * ob; };
+      ConvParams& p = L.p;
+      p.out = oslot(f);
+      if (p.flags & EPI_SHIFT) {
+        p.out_prev = (f > 0) ? oslot(f - 1) : nullptr;
+        p.out_next = oslot(f + 1);
+      }
+      if (l == 10) p.skip = S.ring[b][kRingX1] + (size_t)(f % kRingSlots[kRingX1]) * ring_slot_bytes(kRingX1, H, W);
+      if (l == 13) p.skip = S.ring[b][kRingX0] + (size_t)(f % kRingSlots[kRingX0]) * ring_slot_bytes(kRingX0, H, W);
+      if (l == 15 && b == 0) p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
+      if (l == 15 && b == 1) {
+        p.skip = S.ring[0][kRingM] + (size_t)(f % kRingSlots[kRingM]) * ring_slot_bytes(kRingM, H, W);
+        p.out = out;
+        if (produced) *produced = 1;
+      }
+      if (launch_stage(L, st)) return 1;
+      ++launches;
+    }
+  ++S.step;
+  h->last_launches = launches;
+  return 0;
 }
 
 int bsvd_reset(bsvd_handle* h) {
   if (!h) return fail("null handle");
+  h->stream.step = 0;
+  h->stream.n_in = 0;
+  h->stream.ended = false;
   return 0;
 }
 

@@ -156,3 +156,87 @@ def test_temporal_linearity_property_full_size():
         b = net(x2[None].cuda())[0]
     assert torch.equal(a[17:], b[17:])
     assert not torch.equal(a[:8], b[:8])
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming mode: feedin_one_element / reset (bsvd_arch.py:485-488, 459-461) through
+# bsvd_stream_push — same None protocol, same numbers as the clip schedule
+# ------------------------------------------------------------------------------------------------
+def _drive_stream(net, x, extra_none=0):
+    outs = [net.feedin_one_element(x[i:i + 1].cuda()) for i in range(x.shape[0])]
+    calls = x.shape[0]
+    while sum(o is not None for o in outs) < x.shape[0]:
+        outs.append(net.feedin_one_element(None))
+        calls += 1
+    for _ in range(extra_none):
+        assert net.feedin_one_element(None) is None
+    return outs, calls
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 7, 20])
+def test_stream_protocol_and_values(T):
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(T, 24, 40, seed=21)
+    net.reset()
+    with torch.no_grad():
+        outs, calls = _drive_stream(net, x, extra_none=2)
+        net.reset()
+        clip = net(x[None].cuda())[0]
+    first = next(i for i, o in enumerate(outs) if o is not None)
+    assert first == 16 == net.shift_num           # golden: first_output_call
+    assert calls == T + 16                        # golden: calls_to_drain
+    assert all(o is None for o in outs[:16])
+    y = torch.cat([o for o in outs if o is not None], dim=0)
+    assert y.shape == (T, 3, 24, 40)
+    # the streaming schedule runs the very same kernels on the same operands: bit-identical
+    assert torch.equal(y, clip)
+    ref = O.StreamOracle(layers).streaming_forward(x)
+    assert float((y.float().cpu() - ref).abs().max()) <= TOL["fp16"]
+
+
+def test_stream_matches_reference_fixture_protocol():
+    g = np.load(GOLDEN[-1])    # trained_like_T6_32x48
+    net, _ = make_net(int(g["param_seed"]), float(g["weight_scale"]))
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    net.reset()
+    with torch.no_grad():
+        outs, calls = _drive_stream(net, x)
+    assert next(i for i, o in enumerate(outs) if o is not None) == int(g["first_output_call"])
+    assert calls == int(g["calls_to_drain"])
+    y = torch.cat([o for o in outs if o is not None], dim=0).float().cpu()
+    assert float((y - torch.from_numpy(g["y_stream"])).abs().max()) <= TOL["fp16"]
+
+
+def test_stream_reset_and_reuse_and_noise_map_argument():
+    net, _ = make_net()
+    a, _ = O.make_synthetic_clip(3, 16, 24, seed=31)
+    b, _ = O.make_synthetic_clip(4, 16, 24, seed=32)
+    with torch.no_grad():
+        net.reset()
+        oa, _ = _drive_stream(net, a)
+        net.reset()
+        ob, _ = _drive_stream(net, b)
+        net.reset()
+        oa2 = []
+        for i in range(3):   # 3-channel frame + separate noise map
+            oa2.append(net.feedin_one_element(a[i:i + 1, :3].cuda(), noise_map=a[i:i + 1, 3:4].cuda()))
+        while sum(o is not None for o in oa2) < 3:
+            oa2.append(net.feedin_one_element(None))
+        ca = net(a[None].cuda())[0]
+        cb = net(b[None].cuda())[0]
+    cat = lambda o: torch.cat([t for t in o if t is not None], dim=0)  # noqa: E731
+    assert torch.equal(cat(oa), ca) and torch.equal(cat(ob), cb) and torch.equal(cat(oa2), ca)
+
+
+def test_stream_rejects_frame_after_end_marker():
+    from bsvd_b200.capi import BsvdError
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(2, 16, 16, seed=33)
+    net.reset()
+    net.feedin_one_element(x[:1].cuda())
+    net.feedin_one_element(None)
+    with pytest.raises(BsvdError):
+        net.feedin_one_element(x[1:2].cuda())
+    net.reset()
+    assert net.feedin_one_element(x[:1].cuda()) is None
+    net.reset()
