@@ -361,6 +361,13 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: the driver launches torchrun itself; do the same when called bare
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     else:
         run_b200(args)
 
