@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -87,6 +88,22 @@ static int make_map_s2(CUtensorMap* m, const void* base, int T, int H, int W, in
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(s2) failed: %d", (int)r);
+  return 0;
+}
+
+// Packed weights as a 2-D tensor [rows][64] (rows of 128 B, already swizzled by the host): the CTA-pair
+// kernels fetch half of a filter slab per CTA with a TMA that can signal the leader CTA's barrier.
+static int make_map_w(CUtensorMap* m, const void* base, size_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)kChunk, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kChunk * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return 0;
 }
 
@@ -216,33 +233,52 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr size_t kSmemOptIn = 232448 - 3072;
 constexpr size_t kStagingBytes = 8 * kStageBytesPerWarp;   // epilogue staging of the 8 epilogue warps
 
-template <int NTILE, int R, bool BF16>
-static int launch_inst(const CUtensorMap& map, const ConvParams& p, int grid, size_t smem,
-                       cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<NTILE, R, BF16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
-    attr_done = true;
-  }
-  conv3x3_tc_kernel<NTILE, R, BF16><<<grid, kThreads, smem, st>>>(map, p);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-template <int NTILE, int R>
-static int launch_one(const CUtensorMap& map, const ConvParams& p, int grid, size_t smem,
-                      cudaStream_t st) {
-  return (p.flags & EPI_BF16) ? launch_inst<NTILE, R, true>(map, p, grid, smem, st)
-                              : launch_inst<NTILE, R, false>(map, p, grid, smem, st);
-}
-
+struct StageLaunch;
+template <int NTILE, int R, bool BF16, bool CTA2>
+static int launch_inst(const StageLaunch& L, cudaStream_t st);
 struct StageLaunch {
-  CUtensorMap map;
+  CUtensorMap map;      // activations
+  CUtensorMap map_w;    // packed weights (CTA-pair kernels)
   ConvParams p;
   int grid = 0;
   size_t smem = 0;
   int ntile = 0, rows = 0;
+  int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
 };
+
+template <int NTILE, int R, bool BF16, bool CTA2>
+static int launch_inst(const StageLaunch& L, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2>;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CTA2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.p));
+  return 0;
+}
+template <int NTILE, int R>
+static int launch_one(const StageLaunch& L, cudaStream_t st) {
+  const bool bf = (L.p.flags & EPI_BF16) != 0;
+  if constexpr (NTILE == 16) {
+    return bf ? launch_inst<NTILE, R, true, false>(L, st) : launch_inst<NTILE, R, false, false>(L, st);
+  } else {
+    if (L.cta2) return bf ? launch_inst<NTILE, R, true, true>(L, st) : launch_inst<NTILE, R, false, true>(L, st);
+    return bf ? launch_inst<NTILE, R, true, false>(L, st) : launch_inst<NTILE, R, false, false>(L, st);
+  }
+}
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -256,11 +292,24 @@ static int num_sms() {
 }
 
 // Build the launch record (tensor map + params) of one stage for concrete tensors.
+static int use_cta2_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BSVD_B200_NO_CTA2");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v;
+}
+
 static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_variant,
                       StageLaunch* L) {
   const StageSpec& s = sd.spec;
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
+  // CTA pairs (cta_group::2): one M=256 MMA drives two pixel tiles and each CTA stages only half
+  // of the filter slab.  The 3-channel output stage (N=16) stays single-CTA.
+  const int cta2 = (s.ntile != 16 && use_cta2_default() && !(desc_variant & 32)) ? 1 : 0;
+  L->cta2 = cta2;
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;
@@ -269,10 +318,11 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
   p.xblocks = (Wo + kRunPx - 1) / kRunPx;
   p.yblocks = (Ho + s.rows - 1) / s.rows;
-  p.total_tiles = p.T * p.yblocks * p.xblocks * p.n_tiles;
+  p.positions = p.T * p.yblocks * p.xblocks;
+  p.total_tiles = (cta2 ? (p.positions + 1) / 2 : p.positions) * p.n_tiles;
   p.mode = (s.stride == 2) ? 1 : 0;
   p.cin_total = s.cin;
-  p.w_stage_bytes = (uint32_t)s.ntile * 128u;
+  p.w_stage_bytes = (uint32_t)s.ntile * 128u / (cta2 ? 2u : 1u);
   const size_t budget = kSmemOptIn - 1024 - kStagingBytes;   // minus alignment slack and staging
   if (p.mode == 0) {
     p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
@@ -323,7 +373,13 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   int rc = (p.mode == 0) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
                          : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
   if (rc) return rc;
-  L->grid = std::min(p.total_tiles, num_sms());
+  if (cta2) {
+    rc = make_map_w(&L->map_w, sd.wpack, s.pack_elems() / kChunk, s.ntile / 2);
+    if (rc) return rc;
+  } else {
+    L->map_w = L->map;   // unused
+  }
+  L->grid = cta2 ? 2 * std::min(p.total_tiles, num_sms() / 2) : std::min(p.total_tiles, num_sms());
   L->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
             kStagingBytes;
   L->ntile = s.ntile; L->rows = s.rows;
@@ -331,10 +387,10 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
 }
 
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
-  if (L.ntile == 16 && L.rows == 2) return launch_one<16, 2>(L.map, L.p, L.grid, L.smem, st);
-  if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L.map, L.p, L.grid, L.smem, st);
-  if (L.ntile == 128 && L.rows == 2) return launch_one<128, 2>(L.map, L.p, L.grid, L.smem, st);
-  if (L.ntile == 256 && L.rows == 1) return launch_one<256, 1>(L.map, L.p, L.grid, L.smem, st);
+  if (L.ntile == 16 && L.rows == 2) return launch_one<16, 2>(L, st);
+  if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L, st);
+  if (L.ntile == 128 && L.rows == 2) return launch_one<128, 2>(L, st);
+  if (L.ntile == 256 && L.rows == 1) return launch_one<256, 1>(L, st);
   return fail("no kernel instance for NTILE=%d R=%d", L.ntile, L.rows);
 }
 

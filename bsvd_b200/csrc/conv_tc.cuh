@@ -59,7 +59,8 @@ struct ConvParams {
   int n_tiles;          // GEMM N / NTILE
   int tap_begin, tap_end;
   int xblocks, yblocks; // ceil(W/128), ceil(H/R)
-  int total_tiles;
+  int total_tiles;      // 1-CTA: positions*n_tiles; CTA pair: ceil(positions/2)*n_tiles
+  int positions;        // T*yblocks*xblocks pixel tiles
   int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2)
   int cin_total;        // Cin (stride-2 coordinate math)
   // ---- pipeline ----
@@ -202,6 +203,67 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: both CTAs issue their own TMA loads but signal the LEADER
+// CTA's mbarrier (peer bit 24 of the shared::cluster address cleared); the leader issues one MMA
+// that drives both SMs' tensor cores and multicasts the commit to both CTAs' barriers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -228,9 +290,9 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr, int v
 }
 
 // kind::f16 instruction descriptor: D=f32, A=B=fp16|bf16, both K-major, M=128, N=n.
-__host__ __device__ constexpr uint32_t make_idesc(int n, int bf16) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int bf16, int m = kRunPx) {
   return (1u << 4) | (static_cast<uint32_t>(bf16) << 7) | (static_cast<uint32_t>(bf16) << 10) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kRunPx >> 4) << 24);
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float relu6f(float x) { return fminf(fmaxf(x, 0.f), 6.f); }
@@ -265,11 +327,16 @@ __device__ __forceinline__ float load16(const void* p, long long idx) {
 struct TileCoord {
   int nt, t, y0, x0;
 };
+// CTA2: `tile` indexes (pair of neighbouring pixel tiles, n tile); CTA `rank` takes position
+// 2*pair+rank.  A position past the end (odd count) yields t == T: every TMA box is then fully
+// out of bounds (zero fill) and the epilogue stores nothing.
 template <int R>
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int cta2 = 0,
+                                                 int rank = 0) {
   TileCoord c;
   c.nt = tile % p.n_tiles;
   int s = tile / p.n_tiles;
+  if (cta2) s = 2 * s + rank;
   int xb = s % p.xblocks;
   s /= p.xblocks;
   int yb = s % p.yblocks;
@@ -401,10 +468,12 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int NTILE, int R, bool BF16>
+template <int NTILE, int R, bool BF16, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ ConvParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 16 || NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
+  static_assert(!(CTA2 && NTILE == 16), "the 3-channel output stage stays single-CTA");
   constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator buffer
   constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
@@ -416,6 +485,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;      // 0 = leader of the CTA pair
+  const int tile0 = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tstep = CTA2 ? (gridDim.x >> 1) : gridDim.x;
 
   // 1024-byte aligned operand area (swizzle pattern anchor)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -440,37 +512,49 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), kEpiThreads);
+      mbar_init(acc_empty(b), CTA2 ? 2 * kEpiThreads : kEpiThreads);
     }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.n_tiles * NTILE; i += kThreads) bias_s[i] = p.bias[i];
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   const int ntaps = p.tap_end - p.tap_begin;
+  // bytes one stage receives in total (both CTAs of a pair signal the leader's barrier)
+  const uint32_t a_tx = CTA2 ? 2 * p.a_tx_bytes : p.a_tx_bytes;
+  const uint32_t w_tx = CTA2 ? 2 * p.w_stage_bytes : p.w_stage_bytes;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0 && !(p.desc_variant & 16)) {
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       bool first = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<R>(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
+        const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
         for (int c = 0; c < p.cin_chunks; ++c) {
           if (p.mode == 0) {
             mbar_wait(a_empty(sa), pa ^ 1);
-            mbar_expect_tx(a_full(sa), p.a_tx_bytes);
-            tma_load_4d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
-                        tc.y0 - 1, tc.t);
+            if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
+            if constexpr (CTA2)
+              tma_load_4d_2sm(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk,
+                              tc.x0 - 1, tc.y0 - 1, tc.t);
+            else
+              tma_load_4d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
+                          tc.y0 - 1, tc.t);
             if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
           for (int tap = p.tap_begin; tap < p.tap_end; ++tap) {
@@ -480,18 +564,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const int px = (dx == 1) ? 0 : 1, x2 = tc.x0 + ((dx == 0) ? -1 : 0);
               const int py = (dy == 1) ? 0 : 1, y2 = tc.y0 + ((dy == 0) ? -1 : 0);
               mbar_wait(a_empty(sa), pa ^ 1);
-              mbar_expect_tx(a_full(sa), p.a_tx_bytes);
-              tma_load_5d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
-                          px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
+              if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
+              if constexpr (CTA2)
+                tma_load_5d_2sm(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
+                                px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
+              else
+                tma_load_5d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
+                            px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
               if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
             }
             if (!p.w_resident || first) {
               mbar_wait(w_empty(sw), pw ^ 1);
-              mbar_expect_tx(w_full(sw), p.w_stage_bytes);
-              const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
-                  (static_cast<size_t>(tc.nt * p.cin_chunks + c) * ntaps + (tap - p.tap_begin)) *
-                      p.w_stage_bytes;
-              bulk_load(w_base + sw * p.w_stage_bytes, src, p.w_stage_bytes, w_full(sw));
+              if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
+              const size_t blk = static_cast<size_t>(tc.nt * p.cin_chunks + c) * ntaps + (tap - p.tap_begin);
+              if constexpr (CTA2) {
+                // each CTA of the pair stages half of the N rows of this (chunk, tap) filter slab
+                tma_load_2d_2sm(w_base + sw * p.w_stage_bytes, &map_w, w_full(sw), 0,
+                                static_cast<int>(blk) * NTILE + static_cast<int>(rank) * (NTILE / 2));
+              } else {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + blk * p.w_stage_bytes;
+                bulk_load(w_base + sw * p.w_stage_bytes, src, p.w_stage_bytes, w_full(sw));
+              }
               if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
             }
           }
@@ -504,67 +597,78 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // The whole warp walks the (uniform) tile/chunk/tap loops and waits on the barriers; one
     // elected lane issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are built
     // once; per MMA only the 32-bit start-address word changes by a compile-time constant.
-    const uint32_t idesc = make_idesc(NTILE, BF16 ? 1 : 0);
-    const uint32_t leader = elect_one();
-    constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);  // SW128, version 1, SBO 1024
-    const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
-    const bool skip_mma = (p.desc_variant & 2) != 0;
-    const bool no_load = (p.desc_variant & 16) != 0;
-    uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(acc_empty(buf), acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-      for (int c = 0; c < p.cin_chunks; ++c) {
-        if (p.mode == 0 && !no_load) {
-          mbar_wait(a_full(sa), pa);
-          tc_fence_after();
-        }
+    // In a CTA pair only the leader's warp issues: one M=256 instruction covers both pixel tiles.
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(NTILE, BF16 ? 1 : 0, CTA2 ? 256 : 128);
+      const uint32_t leader = elect_one();
+      constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);  // SW128, version 1, SBO 1024
+      const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
+      const bool skip_mma = (p.desc_variant & 2) != 0;
+      const bool no_load = (p.desc_variant & 16) != 0;
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      uint32_t it = 0;
+      for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(acc_empty(buf), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+        for (int c = 0; c < p.cin_chunks; ++c) {
+          if (p.mode == 0 && !no_load) {
+            mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+          }
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          if (tap < p.tap_begin || tap >= p.tap_end) continue;
-          if (p.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
-          if ((!p.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
-          tc_fence_after();
-          const int dy = tap / 3, dx = tap % 3;
-          // start-address words (>>4) of this stage; LBO field = 1 (unused for SW128 K-major)
-          const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t b_lo0 = (((w_base + sw * p.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t first = (c == 0 && tap == p.tap_begin) ? 0u : 1u;
-          if (leader && !skip_mma) {
+          for (int tap = 0; tap < 9; ++tap) {
+            if (tap < p.tap_begin || tap >= p.tap_end) continue;
+            if (p.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
+            if ((!p.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
+            tc_fence_after();
+            const int dy = tap / 3, dx = tap % 3;
+            // start-address words (>>4) of this stage; LBO field = 1 (unused for SW128 K-major)
+            const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = (((w_base + sw * p.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t first = (c == 0 && tap == p.tap_begin) ? 0u : 1u;
+            if (leader && !skip_mma) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const uint32_t a_off = (p.mode == 0 && !(p.desc_variant & 8))
-                  ? static_cast<uint32_t>(((r + dy) * kHaloPx + dx) * 8)
-                  : static_cast<uint32_t>(r * (kRunPx * 8));
+              for (int r = 0; r < R; ++r) {
+                const uint32_t a_off = (p.mode == 0 && !(p.desc_variant & 8))
+                    ? static_cast<uint32_t>(((r + dy) * kHaloPx + dx) * 8)
+                    : static_cast<uint32_t>(r * (kRunPx * 8));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = desc_hi | (a_lo0 + a_off + k * 2u);
-                const uint64_t bd = desc_hi | (b_lo0 + k * 2u);
-                umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, (k > 0) ? 1u : first);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = desc_hi | (a_lo0 + a_off + k * 2u);
+                  const uint64_t bd = desc_hi | (b_lo0 + k * 2u);
+                  if constexpr (CTA2)
+                    umma_f16_2sm(tmem_acc + r * NTILE, ad, bd, idesc, (k > 0) ? 1u : first);
+                  else
+                    umma_f16(tmem_acc + r * NTILE, ad, bd, idesc, (k > 0) ? 1u : first);
+                }
               }
             }
+            if (leader) {
+              if constexpr (CTA2) {
+                if (!p.w_resident) umma_commit_2sm(w_empty(sw));
+                if (p.mode == 1) umma_commit_2sm(a_empty(sa));
+              } else {
+                if (!p.w_resident) umma_commit(w_empty(sw));
+                if (p.mode == 1) umma_commit(a_empty(sa));
+              }
+            }
+            __syncwarp();
+            if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+            if (p.mode == 1) {
+              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            }
           }
-          if (leader) {
-            if (!p.w_resident) umma_commit(w_empty(sw));
-            if (p.mode == 1) umma_commit(a_empty(sa));
-          }
-          __syncwarp();
-          if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
-          if (p.mode == 1) {
+          if (p.mode == 0) {
+            if (leader) { if constexpr (CTA2) umma_commit_2sm(a_empty(sa)); else umma_commit(a_empty(sa)); }
+            __syncwarp();
             if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
-        if (p.mode == 0) {
-          if (leader) umma_commit(a_empty(sa));
-          __syncwarp();
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
-        }
+        if (leader) { if constexpr (CTA2) umma_commit_2sm(acc_full(buf)); else umma_commit(acc_full(buf)); }
+        __syncwarp();
       }
-      if (leader) umma_commit(acc_full(buf));
-      __syncwarp();
     }
   } else {
     // ======================================= epilogue =======================================
@@ -574,22 +678,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile<R>(p, tile);
+    for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
+      const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
+      // accumulator drained: the (leader's) MMA warp may reuse the buffer
+      auto release_acc = [&]() {
+        tc_fence_before();
+        if constexpr (CTA2) mbar_arrive_cluster(acc_empty(buf), 0); else mbar_arrive(acc_empty(buf));
+      };
+      const bool live = tc.t < p.T;            // false only for the padding tile of an odd pair
       if constexpr (NTILE == 16) {
         // temp2 outc.3 + residual (bsvd_arch.py:394, 408-414): fp32 NCHW out = temp1_out[:, :3] - conv[:, :3]
         const int r = half;                    // R == 2: one row per warp half
         uint32_t v[32];
         tmem_ld16(tacc + r * NTILE, v);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(acc_empty(buf));
+        release_acc();
         const int x = tc.x0 + quad * 32 + lane, y = tc.y0 + r;
-        if (x < p.W && y < p.H) {
+        if (live && x < p.W && y < p.H) {
           const long long plane = static_cast<long long>(p.H) * p.W;
           const long long pix = static_cast<long long>(y) * p.W + x;
           float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane + pix;
@@ -607,6 +716,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         static_assert(kUnits % 2 == 0, "units must split evenly over the two warp halves");
         const int u0 = half * kMine;
         const int nb0 = tc.nt * NTILE;         // global GEMM column of this tile's first column
+        const bool work = live && !(p.desc_variant & 4);
         uint32_t va[32], vb[32];
         tmem_ld32(tacc + (u0 / G) * NTILE + (u0 % G) * 32, va);
 #pragma unroll
@@ -616,10 +726,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int u = u0 + k + 1;
             tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
           } else {
-            tc_fence_before();
-            mbar_arrive(acc_empty(buf));       // accumulator drained: MMA may reuse the buffer
+            release_acc();
           }
-          if (!(p.desc_variant & 4)) {
+          if (work) {
             const int u = u0 + k;
             epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, bias_s, stg, quad, lane);
           }
@@ -629,11 +738,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const int u = u0 + k + 2;
               tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
             } else {
-              tc_fence_before();
-              mbar_arrive(acc_empty(buf));
+              release_acc();
             }
             const int u = u0 + k + 1;
-            if (!(p.desc_variant & 4))
+            if (work)
               epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, bias_s, stg, quad, lane);
           }
         }
@@ -642,12 +750,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(kTmemCols)
-                 : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
