@@ -234,7 +234,7 @@ constexpr size_t kSmemOptIn = 232448 - 3072;
 constexpr size_t kStagingBytes = 8 * kStageBytesPerWarp;   // epilogue staging of the 8 epilogue warps
 
 struct StageLaunch;
-template <int NTILE, int R, bool BF16, bool CTA2>
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
 static int launch_inst(const StageLaunch& L, cudaStream_t st);
 struct StageLaunch {
   CUtensorMap map;      // activations
@@ -246,10 +246,10 @@ struct StageLaunch {
   int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
 };
 
-template <int NTILE, int R, bool BF16, bool CTA2>
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2>;
+  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK>;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     attr_done = true;
@@ -269,15 +269,29 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.p));
   return 0;
 }
+// Epilogue feature sets the kernels are specialised for; a stage runs on the smallest set that
+// covers its flags (the single-CTA debug path only has the general instance).
+constexpr int kMaskPlain = EPI_RELU6;
+constexpr int kMaskShift = EPI_RELU6 | EPI_SHIFT;
+constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
+constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
+template <int NTILE, int R, bool BF16>
+static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
+  if constexpr (NTILE == 16) {
+    return launch_inst<NTILE, R, BF16, false, 0>(L, st);
+  } else {
+    if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll>(L, st);
+    const int f = L.p.flags & kMaskAll;
+    if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain>(L, st);
+    if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift>(L, st);
+    if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid>(L, st);
+    return launch_inst<NTILE, R, BF16, true, kMaskAll>(L, st);
+  }
+}
 template <int NTILE, int R>
 static int launch_one(const StageLaunch& L, cudaStream_t st) {
-  const bool bf = (L.p.flags & EPI_BF16) != 0;
-  if constexpr (NTILE == 16) {
-    return bf ? launch_inst<NTILE, R, true, false>(L, st) : launch_inst<NTILE, R, false, false>(L, st);
-  } else {
-    if (L.cta2) return bf ? launch_inst<NTILE, R, true, true>(L, st) : launch_inst<NTILE, R, false, true>(L, st);
-    return bf ? launch_inst<NTILE, R, true, false>(L, st) : launch_inst<NTILE, R, false, false>(L, st);
-  }
+  return (L.p.flags & EPI_BF16) ? launch_dtype<NTILE, R, true>(L, st)
+                                : launch_dtype<NTILE, R, false>(L, st);
 }
 
 static int g_num_sms = 0;

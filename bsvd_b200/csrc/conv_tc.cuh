@@ -41,6 +41,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kStageBytesPerWarp = 2048;   // epilogue staging: [32 px][32 ch] 16-bit per warp
 constexpr int kMaxBias = 512;
 
+// masks of epilogue features a kernel instance is compiled with
 enum : int {
   EPI_RELU6 = 1,
   EPI_PIXSHUF = 2,
@@ -353,12 +354,53 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 //   phase 2 (lane = 16-byte chunk): read back transposed so that 4 lanes cover one pixel's 64
 //            contiguous bytes, route to the destination frame/sub-pixel and store.
 // --------------------------------------------------------------------------------------------
+// packed ReLU6 on two 16-bit values: clamp(round(x)) == round(clamp(x)) because 0 and 6 are exact
 template <bool BF16>
+__device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+    h = __hmin2(__hmax2(h, __float2bfloat162_rn(0.f)), __float2bfloat162_rn(6.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(6.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// Skip-tensor operand of one unit (lane = pixel): 64 contiguous bytes at the (PixelShuffle-
+// scattered) output location.  Issued one unit ahead of its use so the L2 round trip overlaps the
+// arithmetic of the previous unit.
+template <int MASK>
+__device__ __forceinline__ void skip_prefetch(const ConvParams& p, const TileCoord& tc, int y,
+                                              int nbase, int quad, int lane, uint4 (&sk)[4]) {
+  if constexpr ((MASK & EPI_SKIP) != 0) {
+    const int x = tc.x0 + quad * 32 + lane;
+    if ((p.flags & EPI_SKIP) && tc.t < p.T && x < p.W && y < p.H) {
+      int c0 = nbase, oy = y, ox = x;
+      if (p.flags & EPI_PIXSHUF) {
+        const int q = nbase / p.out_C;
+        c0 = nbase - q * p.out_C;
+        oy = 2 * y + (q >> 1);
+        ox = 2 * x + (q & 1);
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
+          (static_cast<long long>(oy) * p.out_W + ox) * p.skip_C + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sk[j] = __ldg(src + j);
+    }
+  }
+}
+
+// MASK = set of EPI_* features compiled into this instance (runtime flags are a subset of it).
+template <bool BF16, int MASK>
 __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoord& tc, int y,
                                               int nbase, const uint32_t (&v)[32],
+                                              const uint4 (&sk)[4],
                                               const float* bias_s, uint32_t stg, int quad,
                                               int lane) {
-  const int flags = p.flags;
+  const int flags = p.flags & MASK;
   // ------------------------------ phase 1 ------------------------------
   {
     const int x = tc.x0 + quad * 32 + lane;
@@ -372,38 +414,32 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
       f[2] = __uint_as_float(v[8 * j + 2]) + ba.z; f[3] = __uint_as_float(v[8 * j + 3]) + ba.w;
       f[4] = __uint_as_float(v[8 * j + 4]) + bb.x; f[5] = __uint_as_float(v[8 * j + 5]) + bb.y;
       f[6] = __uint_as_float(v[8 * j + 6]) + bb.z; f[7] = __uint_as_float(v[8 * j + 7]) + bb.w;
-      if ((flags & EPI_SKIP) && valid) {
-        const int n0 = nbase + 8 * j;
-        int c0 = n0, oy = y, ox = x;
-        if (flags & EPI_PIXSHUF) {
-          const int q = n0 / p.out_C;
-          c0 = n0 - q * p.out_C;
-          oy = 2 * y + (q >> 1);
-          ox = 2 * x + (q & 1);
+      if constexpr ((MASK & EPI_SKIP) != 0) {
+        if ((flags & EPI_SKIP) && valid) {
+          const uint4 s = sk[j];
+          const float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
+                       d = unpack2<BF16>(s.w);
+          f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+          f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
         }
-        const uint4 s = __ldg(reinterpret_cast<const uint4*>(
-            reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
-            (static_cast<long long>(oy) * p.out_W + ox) * p.skip_C + c0));
-        const float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
-                     d = unpack2<BF16>(s.w);
-        f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
-        f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
       }
-      if (flags & EPI_RELU6) {
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid) {
+          // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
+          const long long plane = static_cast<long long>(p.H) * p.W;
+          const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
+                           static_cast<long long>(y) * p.W + x;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = relu6f(f[i]);
-      }
-      if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid) {
-        // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
-        const long long plane = static_cast<long long>(p.H) * p.W;
-        const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
-                         static_cast<long long>(y) * p.W + x;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+          for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+        }
       }
       uint4 o;
       o.x = pack2<BF16>(f[0], f[1]); o.y = pack2<BF16>(f[2], f[3]);
       o.z = pack2<BF16>(f[4], f[5]); o.w = pack2<BF16>(f[6], f[7]);
+      if (flags & EPI_RELU6) {
+        o.x = relu6_packed<BF16>(o.x); o.y = relu6_packed<BF16>(o.y);
+        o.z = relu6_packed<BF16>(o.z); o.w = relu6_packed<BF16>(o.w);
+      }
       const uint32_t a = stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
                    "r"(o.z), "r"(o.w) : "memory");
@@ -415,50 +451,61 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
     const int j = lane & 3;
     const int n0 = nbase + 8 * j;
     int c0 = n0, q = 0;
-    if (flags & EPI_PIXSHUF) {
-      q = n0 / p.out_C;
-      c0 = n0 - q * p.out_C;
+    if constexpr ((MASK & EPI_PIXSHUF) != 0) {
+      if (flags & EPI_PIXSHUF) {
+        q = n0 / p.out_C;
+        c0 = n0 - q * p.out_C;
+      }
     }
     // fold routing of this 8-channel group (ShiftConv.forward, bsvd_arch.py:42-50): the consumer
     // conv of frame u reads channels [0,f) of frame u+1 and [f,2f) of frame u-1, so the producer
     // of frame t stores those folds straight into the tensors of frames t-1 / t+1.
     uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + tc.t * p.out_frame_stride;
     uint16_t* zdst = nullptr;       // own-frame location that must read as zero (clip ends)
-    if (flags & EPI_SHIFT) {
-      uint16_t* own = dst;
-      if (c0 < p.fold) {
-        if (p.ring_mode) {
-          dst = reinterpret_cast<uint16_t*>(p.out_prev);
-          if (flags & EPI_ZERO_FUTURE) zdst = own;
-        } else {
-          dst = (tc.t > 0) ? own - p.out_frame_stride : nullptr;
-          if (tc.t == p.T - 1) zdst = own;
-        }
-      } else if (c0 < 2 * p.fold) {
-        if (p.ring_mode) {
-          dst = reinterpret_cast<uint16_t*>(p.out_next);
-          if (!p.out_prev) zdst = own;
-        } else {
-          dst = (tc.t + 1 < p.T) ? own + p.out_frame_stride : nullptr;
-          if (tc.t == 0) zdst = own;
+    if constexpr ((MASK & EPI_SHIFT) != 0) {
+      if (flags & EPI_SHIFT) {
+        uint16_t* own = dst;
+        if (c0 < p.fold) {
+          if (p.ring_mode) {
+            dst = reinterpret_cast<uint16_t*>(p.out_prev);
+            if (p.flags & EPI_ZERO_FUTURE) zdst = own;
+          } else {
+            dst = (tc.t > 0) ? own - p.out_frame_stride : nullptr;
+            if (tc.t == p.T - 1) zdst = own;
+          }
+        } else if (c0 < 2 * p.fold) {
+          if (p.ring_mode) {
+            dst = reinterpret_cast<uint16_t*>(p.out_next);
+            if (!p.out_prev) zdst = own;
+          } else {
+            dst = (tc.t + 1 < p.T) ? own + p.out_frame_stride : nullptr;
+            if (tc.t == 0) zdst = own;
+          }
         }
       }
     }
-    const int oy = (flags & EPI_PIXSHUF) ? 2 * y + (q >> 1) : y;
-    const long long rowoff = static_cast<long long>(oy) * p.out_W;
+    const bool ps = ((MASK & EPI_PIXSHUF) != 0) && (flags & EPI_PIXSHUF);
+    const int oy = ps ? 2 * y + (q >> 1) : y;
+    const int xl = tc.x0 + quad * 32 + (lane >> 2);          // x of this lane's pixel for i == 0
+    // element offset of (oy, x(i), c0): off0 + i * step
+    const int ox0 = ps ? 2 * xl + (q & 1) : xl;
+    const long long off0 = (static_cast<long long>(oy) * p.out_W + ox0) * p.out_C + c0;
+    const int step = (ps ? 16 : 8) * p.out_C;
+    const bool row_ok = y < p.H;
+    uint32_t a0 = stg + (lane >> 2) * 64;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pl = 8 * i + (lane >> 2);
-      const uint32_t a = stg + pl * 64 + ((j ^ ((pl >> 1) & 3)) << 4);
+      const uint32_t a = a0 + i * 512 + ((j ^ ((pl >> 1) & 3)) << 4);
       uint4 o;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(a) : "memory");
-      const int x = tc.x0 + quad * 32 + pl;
-      if (x < p.W && y < p.H) {
-        const int ox = (flags & EPI_PIXSHUF) ? 2 * x + (q & 1) : x;
-        const long long off = (rowoff + ox) * p.out_C + c0;
+      if (row_ok && xl + 8 * i < p.W) {
+        const long long off = off0 + static_cast<long long>(i) * step;
         if (dst) *reinterpret_cast<uint4*>(dst + off) = o;
-        if (zdst) *reinterpret_cast<uint4*>(zdst + off) = make_uint4(0, 0, 0, 0);
+        if constexpr ((MASK & EPI_SHIFT) != 0) {
+          if (zdst) *reinterpret_cast<uint4*>(zdst + off) = make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
@@ -468,7 +515,7 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int NTILE, int R, bool BF16, bool CTA2>
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ ConvParams p) {
@@ -512,7 +559,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), CTA2 ? 2 * kEpiThreads : kEpiThreads);
+      mbar_init(acc_empty(b), CTA2 ? 2 * (kEpiThreads / 32) : (kEpiThreads / 32));   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -681,13 +728,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      uint4 ska[4] = {}, skb[4] = {};
+      if constexpr (NTILE != 16) {
+        // skip operand of this warp's first unit: in flight while the MMAs of the tile still run
+        constexpr int G0 = NTILE / 32;
+        const int uf = half * (R * G0 / 2);
+        skip_prefetch<MASK>(p, tc, tc.y0 + uf / G0, tc.nt * NTILE + (uf % G0) * 32, quad, lane, ska);
+      }
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
       // accumulator drained: the (leader's) MMA warp may reuse the buffer
       auto release_acc = [&]() {
         tc_fence_before();
-        if constexpr (CTA2) mbar_arrive_cluster(acc_empty(buf), 0); else mbar_arrive(acc_empty(buf));
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_cluster(acc_empty(buf), 0); else mbar_arrive(acc_empty(buf));
+        }
       };
       const bool live = tc.t < p.T;            // false only for the padding tile of an odd pair
       if constexpr (NTILE == 16) {
@@ -725,24 +782,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (k + 1 < kMine) {
             const int u = u0 + k + 1;
             tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
+            skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
           } else {
             release_acc();
           }
           if (work) {
             const int u = u0 + k;
-            epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, bias_s, stg, quad, lane);
+            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
           }
           if (k + 1 < kMine) {
             tmem_ld_wait();
             if (k + 2 < kMine) {
               const int u = u0 + k + 2;
               tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
+              skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
             } else {
               release_acc();
             }
             const int u = u0 + k + 1;
             if (work)
-              epilogue_unit<BF16>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, bias_s, stg, quad, lane);
+              epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
           }
         }
       }

@@ -22,7 +22,7 @@ def run(name, T, H, W, cin, cout, flags, variant=0, a_stages=0, reps=4):
     by = 2.0 * T * (H * W * cin + Ho * Wo * Co * (2 if flags & K else 1))
     print(f"{name:34s} var={variant} a_st={a_stages}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TF/s  {by/ms/1e6:7.1f} GB/s", flush=True)
 T = 10
-V = (0, 32, 20, 52)   # cta2, 1-cta, cta2 MMA-only, 1-cta MMA-only
+V = (0, 4, 2, 6, 20)   # full, no-epilogue, no-MMA, loads only, MMA only
 for var in V: run("64->64 full", T, 540, 960, 64, 64, R, var)
 for var in V: run("128->128 half shift", T, 270, 480, 128, 128, R | S, var)
 for var in V: run("256->256 quarter shift", T, 135, 240, 256, 256, R | S, var)
