@@ -230,11 +230,24 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    # Each step copies this step's input from pinned host memory and its result back; the
+    # pipelined entry overlaps step i+1's copy-in and step i-1's copy-out with step i's compute
+    # (two host output buffers alternate so no result is overwritten before it is complete).
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    net.denoise_host_async(x_host, out_hosts[0]); net.host_sync()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        net.denoise_host(x_host, out_host=out_host)      # synchronous: returns after the D2H copy
+    for i in range(args.steps):
+        net.denoise_host_async(x_host, out_hosts[i & 1])
+    net.host_sync()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_check = float(out_hosts[(args.steps - 1) & 1].abs().sum())   # touch the last result
+    # synchronous variant (one clip at a time, no overlap) for reference
+    t0s = time.perf_counter()
+    for _ in range(max(2, args.steps // 3)):
+        net.denoise_host(x_host, out_host=out_host)
+    e2e_sync_fps = T_CLIP * max(2, args.steps // 3) / (time.perf_counter() - t0s) * world
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,7 +347,8 @@ def run_b200(args):
                    "weights": "seeded synthetic, 0.5 x kaiming (SURVEY 8d); random init, no checkpoint available"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4),
-                "path": "BSVD.denoise_host -> bsvd_forward_clip_host (pinned host buffers, cudaMemcpyAsync in/out inside the call)"},
+                "path": "BSVD.denoise_host_async -> bsvd_forward_clip_host_async (pinned host buffers; every step's H2D and D2H copies are inside the timed region, overlapped across steps on copy streams)",
+                "unpipelined_value": e2e_sync_fps, "checksum": e2e_check},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -263,6 +263,25 @@ class BSVD(nn.Module):
             out_host.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
         return out_host
 
+    def denoise_host_async(self, input_host, out_host, noise_map_host=None):
+        """Pipelined end-to-end entry (bsvd_forward_clip_host_async): returns after enqueueing;
+        copy-in of the next clip, compute of this one and copy-out of the previous overlap.  Call
+        host_sync() before reading `out_host`.  Buffers must be pinned and stay alive."""
+        assert not input_host.is_cuda and input_host.dtype == torch.float32
+        assert input_host.is_contiguous() and out_host.is_contiguous()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        lib = self._ensure_handle(dev)
+        T, Cc, H, W = input_host.shape
+        nm = noise_map_host
+        capi.check(lib.bsvd_forward_clip_host_async(
+            self._handle, input_host.data_ptr(), nm.data_ptr() if nm is not None else None,
+            out_host.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+        return out_host
+
+    def host_sync(self):
+        if self._handle is not None:
+            capi.check(capi.load_library().bsvd_host_sync(self._handle))
+
     # ---------------------------------------------------------------- streaming mode
     def feedin_one_element(self, x, noise_map=None):
         """One pipeline step (bsvd_arch.py:485-488): x [1,C,H,W] or None -> [1,3,H,W] or None.

@@ -515,6 +515,12 @@ struct bsvd_handle {
   // pinned/device staging for the host entry
   float* d_in = nullptr; float* d_nmap = nullptr; float* d_out = nullptr;
   size_t d_in_bytes = 0, d_nmap_bytes = 0, d_out_bytes = 0;
+  // ---- pipelined host entry (bsvd_forward_clip_host_async): 2-deep staging ----
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+  float* pin[2] = {}; float* pnm[2] = {}; float* pout[2] = {};
+  size_t pin_bytes[2] = {}, pnm_bytes[2] = {}, pout_bytes[2] = {};
+  unsigned long long host_calls = 0;
   // ---- streaming mode (feedin_one_element) ----
   struct StreamLayer {
     StageLaunch tmpl;                 // planned for T=1 on ring slot 0
@@ -575,9 +581,7 @@ static void free_workspace(bsvd_handle* h) {
 static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, float* out, int T,
                            int in_c, int H, int W) {
   const bool same_shape = (h->pT == T && h->pH == H && h->pW == W && h->ws);
-  if (same_shape && h->p_in == in && h->p_nmap == nmap && h->p_out == out && h->p_inc == in_c &&
-      !h->plan.empty())
-    return 0;
+  if (same_shape && !h->plan.empty()) return 0;   // in/out pointers are patched at launch time
   if (!same_shape) {
     free_workspace(h);
     const size_t full = (size_t)T * H * W * 64 * 2;
@@ -684,6 +688,16 @@ int bsvd_destroy(bsvd_handle* h) {
   for (auto& s : h->stages) free_stage(s);
   for (auto& set : h->ev_sets)
     for (auto& e : set) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->pin[i]) cudaFree(h->pin[i]);
+    if (h->pnm[i]) cudaFree(h->pnm[i]);
+    if (h->pout[i]) cudaFree(h->pout[i]);
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+  }
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_nmap) cudaFree(h->d_nmap);
   if (h->d_out) cudaFree(h->d_out);
@@ -774,6 +788,9 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   CUDA_TRY(cudaGetLastError());
   if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   int launches = 1;
+  h->plan[15].p.resid_in = in;          // temp1 residual reads the raw input (skip1)
+  h->plan[15].p.resid_C = in_c;
+  h->plan[BSVD_NUM_LAYERS - 1].p.out = out;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
     if (launch_stage(h->plan[l], st)) return 1;
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[l + 2], st));
@@ -809,6 +826,57 @@ int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nm
     return 1;
   CUDA_TRY(cudaMemcpyAsync(out_host, h->d_out, plane * T * 3, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Pipelined variant: returns after enqueueing.  The H2D copy of call i+1 (own copy stream) overlaps
+// the forward of call i (caller's stream) and the D2H copy of call i-1 (second copy stream); device
+// staging is double-buffered, ordering is by events.  bsvd_host_sync() waits for everything.
+int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const float* nmap_host,
+                                 float* out_host, int T, int in_c, int H, int W, void* stream) {
+  if (!h || !in_host || !out_host) return fail("null argument");
+  if (check_hw(T, in_c, H, W, nmap_host != nullptr)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!h->s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const int k = (int)(h->host_calls & 1);
+  const size_t plane = (size_t)H * W * sizeof(float);
+  if (ensure_dev(&h->pin[k], &h->pin_bytes[k], plane * T * in_c)) return 1;
+  if (ensure_dev(&h->pout[k], &h->pout_bytes[k], plane * T * 3)) return 1;
+  if (nmap_host && ensure_dev(&h->pnm[k], &h->pnm_bytes[k], plane * T)) return 1;
+  if (h->host_calls >= 2) {
+    CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[k], 0));   // forward i-2 has consumed pin[k]
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_d2h[k], 0));          // copy-out i-2 has drained pout[k]
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->pin[k], in_host, plane * T * in_c, cudaMemcpyHostToDevice, h->s_h2d));
+  if (nmap_host)
+    CUDA_TRY(cudaMemcpyAsync(h->pnm[k], nmap_host, plane * T, cudaMemcpyHostToDevice, h->s_h2d));
+  CUDA_TRY(cudaEventRecord(h->ev_h2d[k], h->s_h2d));
+  CUDA_TRY(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
+  if (bsvd_forward_clip(h, h->pin[k], nmap_host ? h->pnm[k] : nullptr, h->pout[k], T, in_c, H, W,
+                        stream))
+    return 1;
+  CUDA_TRY(cudaEventRecord(h->ev_comp[k], st));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[k], 0));
+  CUDA_TRY(cudaMemcpyAsync(out_host, h->pout[k], plane * T * 3, cudaMemcpyDeviceToHost, h->s_d2h));
+  CUDA_TRY(cudaEventRecord(h->ev_d2h[k], h->s_d2h));
+  ++h->host_calls;
+  return 0;
+}
+
+int bsvd_host_sync(bsvd_handle* h) {
+  if (!h) return fail("null handle");
+  if (h->s_d2h) {
+    CUDA_TRY(cudaStreamSynchronize(h->s_h2d));
+    CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+  }
   return 0;
 }
 

@@ -87,6 +87,14 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
 int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* noise_map_host,
                            float* out_host, int T, int in_c, int H, int W, void* stream);
 
+/* Pipelined form of the host entry: enqueues H2D (own copy stream), forward (caller's stream) and
+ * D2H (second copy stream) and returns; consecutive calls overlap copy-in of clip i+1, compute of
+ * clip i and copy-out of clip i-1 (double-buffered device staging).  in_host/out_host must stay
+ * valid (and should be pinned) until bsvd_host_sync() returns. */
+int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const float* noise_map_host,
+                                 float* out_host, int T, int in_c, int H, int W, void* stream);
+int bsvd_host_sync(bsvd_handle* h);
+
 /* -- streaming mode: BSVD.feedin_one_element / reset (bsvd_arch.py:485-488, 459-461) -------
  * frame:     device fp32 [in_c, H, W] or NULL (NULL = the reference's feedin_one_element(None))
  * noise_map: device fp32 [1, H, W] or NULL

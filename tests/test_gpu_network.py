@@ -240,3 +240,16 @@ def test_stream_rejects_frame_after_end_marker():
     net.reset()
     assert net.feedin_one_element(x[:1].cuda()) is None
     net.reset()
+
+
+def test_pipelined_host_entry_matches_and_overlaps_safely():
+    """bsvd_forward_clip_host_async: several clips in flight with alternating host buffers give
+    exactly the synchronous results (double-buffered staging, event ordering)."""
+    net, _ = make_net()
+    clips = [O.make_synthetic_clip(3, 40, 72, seed=40 + i)[0].pin_memory() for i in range(5)]
+    outs = [torch.empty(3, 3, 40, 72).pin_memory() for _ in range(5)]
+    for x, o in zip(clips, outs):
+        net.denoise_host_async(x, o)
+    net.host_sync()
+    for x, o in zip(clips, outs):
+        assert torch.equal(o, net.denoise_host(x))
