@@ -17,6 +17,7 @@
 
 #include "../../include/bsvd_b200.h"
 #include "conv_tc.cuh"
+#include "final_conv.cuh"
 
 namespace bsvd {
 
@@ -151,14 +152,17 @@ struct StageSpec {
   void derive() {
     gemm_n = final_out ? 16 : cout;
     ntile = gemm_n >= 256 ? 256 : gemm_n;
-    rows = (ntile == 256) ? 1 : 2;
+    rows = final_out ? kFinalR : ((ntile == 256) ? 1 : 2);
     cin_chunks = first_im2col ? 1 : cin / kChunk;
     tap_begin = first_im2col ? 4 : 0;
     tap_end = first_im2col ? 5 : 9;
   }
   int ntaps() const { return tap_end - tap_begin; }
   int n_tiles() const { return gemm_n / ntile; }
-  size_t pack_elems() const { return (size_t)n_tiles() * cin_chunks * ntaps() * ntile * kChunk; }
+  size_t pack_elems() const {
+    if (final_out) return (size_t)3 * kFinalN * kChunk;   // [dx][dy*3+co][64]
+    return (size_t)n_tiles() * cin_chunks * ntaps() * ntile * kChunk;
+  }
 };
 
 // GEMM column -> reference output channel (PixelShuffle permutes so that one sub-pixel's channels
@@ -179,6 +183,19 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
   for (int col = 0; col < s.gemm_n; ++col) {
     const int co = col_to_cout(s, col);
     if (co < s.cout) bias[col] = b ? b[co] : 0.f;
+  }
+  if (s.final_out) {
+    // final_conv.cuh layout: slab dx, row n = dy*3 + co, 64 input channels, SW128-swizzled rows
+    for (int dx = 0; dx < 3; ++dx)
+      for (int dy = 0; dy < 3; ++dy)
+        for (int co = 0; co < s.cout; ++co) {
+          const int n = dy * 3 + co;
+          for (int k = 0; k < kChunk; ++k) {
+            const float v = w[((size_t)co * s.cin + k) * 9 + dy * 3 + dx];
+            pack[((size_t)dx * kFinalN + n) * kChunk + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = to16(v, bf16);
+          }
+        }
+    return;
   }
   const int nt_count = s.n_tiles();
   for (int nt = 0; nt < nt_count; ++nt)
@@ -226,6 +243,7 @@ struct StageIO {
   long long skip_frame_stride = 0;
   const float* resid_in = nullptr;
   int resid_C = 0;
+  void* aux_out = nullptr;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -277,9 +295,7 @@ constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
 constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
-  if constexpr (NTILE == 16) {
-    return launch_inst<NTILE, R, BF16, false, 0>(L, st);
-  } else {
+  {
     if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll>(L, st);
     const int f = L.p.flags & kMaskAll;
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain>(L, st);
@@ -332,6 +348,24 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
   p.xblocks = (Wo + kRunPx - 1) / kRunPx;
   p.yblocks = (Ho + s.rows - 1) / s.rows;
+  if (s.final_out) {
+    // dedicated kernel (final_conv.cuh): tiles of 4 output rows, filter bank resident
+    p.n_tiles = 1;
+    p.positions = p.T * p.yblocks * p.xblocks;
+    p.total_tiles = p.positions;
+    p.wpack = sd.wpack; p.bias = sd.bias;
+    p.flags = EPI_FINAL | (bf16 ? EPI_BF16 : 0);
+    p.out = io.out; p.out_C = 3; p.out_H = Ho; p.out_W = Wo;
+    p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
+    if (!io.skip) return fail("stage needs a skip tensor");
+    L->cta2 = 0;
+    if (make_map_halo(&L->map, io.in, io.T, io.H, io.W, s.cin, s.rows)) return 1;
+    L->map_w = L->map;
+    L->grid = std::min(p.total_tiles, num_sms());
+    L->smem = kFinalSmem;
+    L->ntile = 16; L->rows = s.rows;
+    return 0;
+  }
   p.positions = p.T * p.yblocks * p.xblocks;
   p.total_tiles = (cta2 ? (p.positions + 1) / 2 : p.positions) * p.n_tiles;
   p.mode = (s.stride == 2) ? 1 : 0;
@@ -378,7 +412,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   else { p.out_C = s.final_out ? 3 : s.cout; p.out_H = Ho; p.out_W = Wo; }
   p.out_frame_stride = (long long)p.out_H * p.out_W * p.out_C;
   p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
-  p.resid_in = io.resid_in; p.resid_C = io.resid_C;
+  p.resid_in = io.resid_in; p.resid_C = io.resid_C; p.aux_out = io.aux_out;
   p.fold = p.out_C / 8;
   if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
@@ -401,7 +435,18 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
 }
 
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
-  if (L.ntile == 16 && L.rows == 2) return launch_one<16, 2>(L, st);
+  if (L.ntile == 16) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
+      attr_done = true;
+    }
+    if (L.p.flags & EPI_BF16) final_conv_kernel<true><<<L.grid, kThreads, L.smem, st>>>(L.map, L.p);
+    else final_conv_kernel<false><<<L.grid, kThreads, L.smem, st>>>(L.map, L.p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L, st);
   if (L.ntile == 128 && L.rows == 2) return launch_one<128, 2>(L, st);
   if (L.ntile == 256 && L.rows == 1) return launch_one<256, 1>(L, st);
@@ -506,6 +551,7 @@ struct bsvd_handle {
   size_t ws_bytes = 0;
   uint16_t *bufP = nullptr, *bufA = nullptr, *bufX0 = nullptr, *bufM = nullptr;
   uint16_t *bufH0 = nullptr, *bufH1 = nullptr, *bufX1 = nullptr, *bufQ0 = nullptr, *bufQ1 = nullptr;
+  uint16_t* bufS = nullptr;   // compact [T][H][W][4] copy of temp1's output channels 0..3 (skip1 of temp2)
   std::vector<StageLaunch> plan;
   int last_launches = 0;
   // per-stage event timing
@@ -536,6 +582,7 @@ struct bsvd_handle {
     // rings[blk][k] : device base of ring k of DenBlock blk; see kRing* below
     uint8_t* ring[2][kNumRings] = {};
     float* raw = nullptr;             // fp32 [9][4][H][W] ring of the raw network input
+    uint8_t* aux = nullptr;           // 16-bit [9][H][W][4] ring: temp1 output channels 0..3 (skip1 of temp2)
     StreamLayer layers[BSVD_NUM_LAYERS];
   } stream;
 };
@@ -588,7 +635,8 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     const size_t half = (size_t)T * (H / 2) * (W / 2) * 128 * 2;
     const size_t quar = (size_t)T * (H / 4) * (W / 4) * 256 * 2;
     const size_t fa = align_up(full, 1024), ha = align_up(half, 1024), qa = align_up(quar, 1024);
-    h->ws_bytes = 4 * fa + 3 * ha + 2 * qa;
+    const size_t sa = align_up((size_t)T * H * W * 4 * 2, 1024);
+    h->ws_bytes = 4 * fa + 3 * ha + 2 * qa + sa;
     CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
     uint8_t* b = reinterpret_cast<uint8_t*>(h->ws);
     h->bufP = (uint16_t*)b; b += fa;
@@ -600,6 +648,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     h->bufX1 = (uint16_t*)b; b += ha;
     h->bufQ0 = (uint16_t*)b; b += qa;
     h->bufQ1 = (uint16_t*)b; b += qa;
+    h->bufS = (uint16_t*)b; b += sa;
     h->pT = T; h->pH = H; h->pW = W;
   }
   h->p_in = in; h->p_nmap = nmap; h->p_out = out; h->p_inc = in_c;
@@ -612,7 +661,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
       StageIO io;
       io.in = src; io.T = T; io.H = sh; io.W = sw; io.out = dst;
       io.skip = skip; io.skip_C = skip_C; io.skip_frame_stride = skip_fs;
-      if (blk == 0 && l == 15) { io.resid_in = in; io.resid_C = in_c; }
+      if (blk == 0 && l == 15) { io.resid_in = in; io.resid_C = in_c; io.aux_out = h->bufS; }
       return plan_stage(h->stages[blk * 16 + l], io, h->bf16, 0, &h->plan[blk * 16 + l]);
     };
     const void* src0 = (blk == 0) ? (const void*)h->bufP : (const void*)h->bufM;
@@ -633,7 +682,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, 64, fs_full);
     rc |= plan(14, h->bufA, H, W, h->bufP);
     if (blk == 0) rc |= plan(15, h->bufP, H, W, h->bufM);
-    else rc |= plan(15, h->bufP, H, W, out, h->bufM, 64, fs_full);
+    else rc |= plan(15, h->bufP, H, W, out, h->bufS, 4, (long long)H * W * 4);
     if (rc) { h->plan.clear(); return 1; }
   }
   return 0;
@@ -902,10 +951,13 @@ static int build_stream(bsvd_handle* h, int H, int W) {
     for (int k = 0; k < kNumRings; ++k) total += ring_slot_bytes(k, H, W) * kRingSlots[k];
   const size_t raw_bytes = align_up((size_t)9 * 4 * H * W * sizeof(float), 1024);
   total += raw_bytes;
+  const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+  total += 9 * aux_slot;
   CUDA_TRY(cudaMalloc(&S.ws, total));
   S.ws_bytes = total;
   uint8_t* p = reinterpret_cast<uint8_t*>(S.ws);
   S.raw = reinterpret_cast<float*>(p); p += raw_bytes;
+  S.aux = p; p += 9 * aux_slot;
   for (int b = 0; b < 2; ++b)
     for (int k = 0; k < kNumRings; ++k) { S.ring[b][k] = p; p += ring_slot_bytes(k, H, W) * kRingSlots[k]; }
   for (int b = 0; b < 2; ++b)
@@ -927,7 +979,8 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       io.skip = S.ring[b][kRingX0]; io.skip_C = 64;
       io.resid_in = S.raw; io.resid_C = 4;
       if (l == 10) { io.skip = S.ring[b][kRingX1]; io.skip_C = 128; }
-      if (l == 15 && b == 1) { io.skip = S.ring[0][kRingM]; io.skip_C = 64; }
+      if (l == 15 && b == 1) { io.skip = S.aux; io.skip_C = 4; }
+      if (l == 15 && b == 0) io.aux_out = S.aux;
       if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
       const int nslots = kRingSlots[in_ring];
       SL.maps.resize(nslots);
@@ -998,9 +1051,13 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
       }
       if (l == 10) p.skip = S.ring[b][kRingX1] + (size_t)(f % kRingSlots[kRingX1]) * ring_slot_bytes(kRingX1, H, W);
       if (l == 13) p.skip = S.ring[b][kRingX0] + (size_t)(f % kRingSlots[kRingX0]) * ring_slot_bytes(kRingX0, H, W);
-      if (l == 15 && b == 0) p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
+      const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+      if (l == 15 && b == 0) {
+        p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
+        p.aux_out = S.aux + (size_t)(f % 9) * aux_slot;
+      }
       if (l == 15 && b == 1) {
-        p.skip = S.ring[0][kRingM] + (size_t)(f % kRingSlots[kRingM]) * ring_slot_bytes(kRingM, H, W);
+        p.skip = S.aux + (size_t)(f % 9) * aux_slot;
         p.out = out;
         if (produced) *produced = 1;
       }

@@ -87,6 +87,8 @@ struct ConvParams {
   int skip_C;
   const float* resid_in;   // fp32 NCHW raw network input (EPI_RESID_IN)
   int resid_C;
+  void* aux_out;        // EPI_RESID_IN: compact 16-bit [T][H][W][4] copy of output channels 0..3
+                        // (the skip1 operand of temp2's residual: 8 B/px instead of a 128 B row)
   int fold;             // shift fold size in output channels (EPI_SHIFT)
 };
 
@@ -436,6 +438,12 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
       uint4 o;
       o.x = pack2<BF16>(f[0], f[1]); o.y = pack2<BF16>(f[2], f[3]);
       o.z = pack2<BF16>(f[4], f[5]); o.w = pack2<BF16>(f[6], f[7]);
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid && p.aux_out) {
+          const long long pix = (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
+          reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o.x, o.y);
+        }
+      }
       if (flags & EPI_RELU6) {
         o.x = relu6_packed<BF16>(o.x); o.y = relu6_packed<BF16>(o.y);
         o.z = relu6_packed<BF16>(o.z); o.w = relu6_packed<BF16>(o.w);

@@ -1,0 +1,180 @@
+// final_conv.cuh — temp2.outc.convblock.3 (64 -> 3 channels) + residual, fp32 NCHW output
+// (reference: OutputCvBlock's last nn.Conv2d, bsvd_arch.py:295-298, and none_minus :408-414).
+//
+// With only 3 output channels an N=16 MMA per (tap, k-step) is dominated by the fixed cost of
+// fetching its 128x16 A operand from shared memory.  This kernel stacks the three vertical taps
+// into the N dimension instead: for every haloed INPUT row hr it accumulates
+//     D_hr[p, dy*3+co] = sum_dx sum_ci X[hr][p+dx][ci] * W[co][ci][dy][dx]          (12 MMAs/row)
+// and the epilogue finishes the 3x3 sum with three fp32 adds per output:
+//     out[r][p][co] = skip - (D_r[p,co] + D_{r+1}[p,3+co] + D_{r+2}[p,6+co] + bias[co]).
+// Per 4 output rows that is 72 MMAs instead of 144.  Same TMA halo tile, same descriptor-offset
+// trick, same warp roles as conv_tc.cuh; single CTA (there is no filter slab worth sharing).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace bsvd {
+
+constexpr int kFinalR = 4;                       // output rows per tile
+constexpr int kFinalHaloRows = kFinalR + 2;
+constexpr int kFinalN = 16;                      // GEMM N: 9 used columns (dy, co)
+constexpr uint32_t kFinalATx = kFinalHaloRows * kRowBytes;              // 99840
+constexpr uint32_t kFinalAStage = (kFinalATx + 1023u) & ~1023u;         // 100352
+constexpr uint32_t kFinalWStage = kFinalN * 128;                        // one dx slab: 2 KB
+constexpr size_t kFinalSmem = 1024 + 2 * kFinalAStage + 3 * kFinalWStage;
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+final_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ ConvParams p) {
+  constexpr int kAccStride = 128;                // TMEM columns between the two accumulator sets
+  constexpr int kTmemCols = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ float bias_s[4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = a_base + 2 * kFinalAStage;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (4 + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (6 + b); };
+  const uint32_t w_full = bar0 + 8u * 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), kEpiThreads / 32);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 3) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 3 * kFinalWStage);
+      bulk_load(w_base, p.wpack, 3 * kFinalWStage, w_full);
+      uint32_t sa = 0, pa = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<kFinalR>(p, tile);
+        mbar_wait(a_empty(sa), pa ^ 1);
+        mbar_expect_tx(a_full(sa), kFinalATx);
+        tma_load_4d(a_base + sa * kFinalAStage, &map_a, a_full(sa), 0, tc.x0 - 1, tc.y0 - 1, tc.t);
+        if (++sa == 2) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(kFinalN, BF16 ? 1 : 0);
+    const uint32_t leader = elect_one();
+    constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);
+    const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t sa = 0, pa = 0, it = 0;
+    mbar_wait(w_full, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(acc_empty(buf), acc_phase ^ 1);
+      mbar_wait(a_full(sa), pa);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * kAccStride;
+      const uint32_t a_lo0 = (((a_base + sa * kFinalAStage) & 0x3FFFFu) >> 4) | (1u << 16);
+      if (leader) {
+#pragma unroll
+        for (int hr = 0; hr < kFinalHaloRows; ++hr) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = desc_hi | (a_lo0 + static_cast<uint32_t>((hr * kHaloPx + dx) * 8) + k * 2u);
+              const uint64_t bd = desc_hi | (b_lo0 + static_cast<uint32_t>(dx * (kFinalWStage >> 4)) + k * 2u);
+              umma_f16(tmem_acc + hr * kFinalN, ad, bd, idesc, (dx > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(a_empty(sa));
+        umma_commit(acc_full(buf));
+      }
+      __syncwarp();
+      if (++sa == 2) { sa = 0; pa ^= 1; }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile<kFinalR>(p, tile);
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      const int x = tc.x0 + quad * 32 + lane;
+      // skip operand (temp1 output, channels 0..2) of this warp's two rows: in flight during the MMAs
+      uint2 sk[2] = {};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int y = tc.y0 + half + 2 * i;
+        if (x < p.W && y < p.H)
+          sk[i] = __ldg(reinterpret_cast<const uint2*>(
+              reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
+              (static_cast<long long>(y) * p.W + x) * p.skip_C));
+      }
+      mbar_wait(acc_full(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + lane_base + buf * kAccStride;
+      // output row r = half + 2i needs columns [3dy, 3dy+3) of halo row r + dy
+      uint32_t d[2][3][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+          tmem_ld4(tacc + (half + 2 * i + dy) * kFinalN + 3 * dy, d[i][dy]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int y = tc.y0 + half + 2 * i;
+        if (x < p.W && y < p.H) {
+          const float2 s01 = unpack2<BF16>(sk[i].x), s23 = unpack2<BF16>(sk[i].y);
+          const float sv[3] = {s01.x, s01.y, s23.x};
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane +
+                     static_cast<long long>(y) * p.W + x;
+#pragma unroll
+          for (int co = 0; co < 3; ++co) {
+            const float conv = __uint_as_float(d[i][0][co]) + __uint_as_float(d[i][1][co]) +
+                               __uint_as_float(d[i][2][co]) + bias_s[co];
+            o[co * plane] = sv[co] - conv;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace bsvd

@@ -253,3 +253,19 @@ def test_pipelined_host_entry_matches_and_overlaps_safely():
     net.host_sync()
     for x, o in zip(clips, outs):
         assert torch.equal(o, net.denoise_host(x))
+
+
+def test_spatial_tiles_bit_exact():
+    """4K-style spatial tiling (bsvd_b200/tiling.py): every tile processed with an 80-px input ring
+    reproduces the untiled forward bit for bit (same per-pixel operands and summation order)."""
+    from bsvd_b200 import tiling
+    net, _ = make_net()
+    x, _ = O.make_synthetic_clip(3, 184, 408, seed=12)
+    xc = x.cuda()
+    with torch.no_grad():
+        full = net(xc[None])[0]
+        fwd = lambda t: net(t[None])[0]  # noqa: E731
+        assert torch.equal(tiling.forward_tiled_local(fwd, xc, 2, 2), full)
+        assert torch.equal(tiling.forward_tiled_local(fwd, xc, 1, 3), full)
+        # 4 px less than the receptive field is already visible
+        assert not torch.equal(tiling.forward_tiled_local(fwd, xc, 1, 2, halo=76), full)

@@ -1,0 +1,79 @@
+"""Spatial-tile mode (bsvd_b200/tiling.py): plan arithmetic, exactness of the halo argument with
+the CPU oracle as the network, and the world_size-2 exchange path over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bsvd_b200 import tiling
+from oracle import bsvd_oracle as O
+
+
+def test_tile_plan_covers_frame_and_is_aligned():
+    for (H, W, r, c) in [(2160, 3840, 4, 2), (2160, 3840, 2, 4), (540, 960, 1, 2), (136, 264, 2, 3)]:
+        tiles = tiling.tile_plan(H, W, r, c)
+        assert len(tiles) == r * c
+        cover = torch.zeros(H, W, dtype=torch.int32)
+        for t in tiles:
+            cover[t.y0:t.y1, t.x0:t.x1] += 1
+            assert all(v % 4 == 0 for v in (t.y0, t.y1, t.x0, t.x1, t.hy0, t.hy1, t.hx0, t.hx1))
+            assert t.hy0 == max(0, t.y0 - tiling.HALO) and t.hx1 == min(W, t.x1 + tiling.HALO)
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+    with pytest.raises(ValueError):
+        tiling.tile_plan(18, 32, 1, 1)
+
+
+def _oracle_forward():
+    layers = O.layers_from_tsn_state(O.make_synthetic_params(0, 0.5))
+    return lambda x: O.forward_clip(layers, x)
+
+
+def test_halo_is_sufficient_with_oracle_network():
+    """Receptive-field claim behind HALO=80: tiled == untiled for the fp32 oracle (CPU conv picks
+    kernels by shape, so allow fp32 summation-order noise), and a too-small halo is NOT enough."""
+    fwd = _oracle_forward()
+    x, _ = O.make_synthetic_clip(2, 96, 336, seed=5)
+    full = fwd(x)
+    tiled = tiling.forward_tiled_local(fwd, x, 1, 2)
+    assert float((tiled - full).abs().max()) < 2e-5
+    small = tiling.forward_tiled_local(fwd, x, 1, 2, halo=8)
+    assert float((small - full).abs().max()) > 1e-4
+
+
+def _worker(rank, world, port, H, W, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    fwd = _oracle_forward()
+    x, _ = O.make_synthetic_clip(1, H, W, seed=6)
+    t = tiling.tile_plan(H, W, 1, world)[rank]
+    out = tiling.forward_tiled_distributed(fwd, x[:, :, t.y0:t.y1, t.x0:t.x1].contiguous(), H, W,
+                                           1, world)
+    if rank == 0:
+        q.put(out.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_exchange_world2_gloo():
+    H, W = 48, 328
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, H, W, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = torch.from_numpy(q.get(timeout=240))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, _ = O.make_synthetic_clip(1, H, W, seed=6)
+    full = _oracle_forward()(x)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) < 2e-5
