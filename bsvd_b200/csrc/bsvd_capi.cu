@@ -151,7 +151,8 @@ struct StageSpec {
   int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
   void derive() {
     gemm_n = final_out ? 16 : cout;
-    ntile = gemm_n >= 256 ? 256 : gemm_n;
+    static const int ntile_max = [] { const char* e = getenv("BSVD_B200_NTILE_MAX"); return e ? atoi(e) : 256; }();
+    ntile = gemm_n >= 256 ? (ntile_max >= 256 ? 256 : 128) : gemm_n;
     rows = final_out ? kFinalR : ((ntile == 256) ? 1 : 2);
     cin_chunks = first_im2col ? 1 : cin / kChunk;
     tap_begin = first_im2col ? 4 : 0;
@@ -1110,6 +1111,12 @@ int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, con
     L.smem += (size_t)(a_over - L.p.a_stages) * L.p.a_stage_bytes;
     L.p.a_stages = a_over;
     if (L.smem > kSmemOptIn) rc = fail("debug a_stages override exceeds shared memory");
+  }
+  const int w_over = (d->debug_variant >> 16) & 0xf;
+  if (!rc && w_over && !L.p.w_resident) {   // debug: override the number of W stages
+    L.smem += (size_t)(w_over - L.p.w_stages) * L.p.w_stage_bytes;
+    L.p.w_stages = w_over;
+    if (L.smem > kSmemOptIn) rc = fail("debug w_stages override exceeds shared memory");
   }
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
   cudaEvent_t e0, e1;

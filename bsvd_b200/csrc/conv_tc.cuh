@@ -376,21 +376,27 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 template <int MASK>
 __device__ __forceinline__ void skip_prefetch(const ConvParams& p, const TileCoord& tc, int y,
                                               int nbase, int quad, int lane, uint4 (&sk)[4]) {
+  // Coalesced layout (same as the store phase): lane = (pixel group lane>>2, 16-byte chunk lane&3),
+  // so four lanes fetch the 64 contiguous bytes of one pixel: full sectors, 8 lines per request.
   if constexpr ((MASK & EPI_SKIP) != 0) {
-    const int x = tc.x0 + quad * 32 + lane;
-    if ((p.flags & EPI_SKIP) && tc.t < p.T && x < p.W && y < p.H) {
-      int c0 = nbase, oy = y, ox = x;
-      if (p.flags & EPI_PIXSHUF) {
-        const int q = nbase / p.out_C;
-        c0 = nbase - q * p.out_C;
-        oy = 2 * y + (q >> 1);
-        ox = 2 * x + (q & 1);
+    if ((p.flags & EPI_SKIP) && tc.t < p.T && y < p.H) {
+      const int j = lane & 3;
+      const int n0 = nbase + 8 * j;
+      int c0 = n0, q = 0;
+      const bool ps = (p.flags & EPI_PIXSHUF) != 0;
+      if (ps) {
+        q = n0 / p.out_C;
+        c0 = n0 - q * p.out_C;
       }
-      const uint4* src = reinterpret_cast<const uint4*>(
-          reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
-          (static_cast<long long>(oy) * p.out_W + ox) * p.skip_C + c0);
+      const int oy = ps ? 2 * y + (q >> 1) : y;
+      const int xl = tc.x0 + quad * 32 + (lane >> 2);
+      const int ox0 = ps ? 2 * xl + (q & 1) : xl;
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
+                            (static_cast<long long>(oy) * p.out_W + ox0) * p.skip_C + c0;
+      const int step = (ps ? 16 : 8) * p.skip_C;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sk[j] = __ldg(src + j);
+      for (int i = 0; i < 4; ++i)
+        if (xl + 8 * i < p.W) sk[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * step));
     }
   }
 }
@@ -403,6 +409,21 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
                                               const float* bias_s, uint32_t stg, int quad,
                                               int lane) {
   const int flags = p.flags & MASK;
+  // ------------------------------ phase 0 ------------------------------
+  // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
+  if constexpr ((MASK & EPI_SKIP) != 0) {
+    if (flags & EPI_SKIP) {
+      const int j = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pl = 8 * i + (lane >> 2);
+        const uint32_t a = stg + pl * 64 + ((j ^ ((pl >> 1) & 3)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(sk[i].x), "r"(sk[i].y),
+                     "r"(sk[i].z), "r"(sk[i].w) : "memory");
+      }
+      __syncwarp();
+    }
+  }
   // ------------------------------ phase 1 ------------------------------
   {
     const int x = tc.x0 + quad * 32 + lane;
@@ -418,7 +439,10 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
       f[6] = __uint_as_float(v[8 * j + 6]) + bb.z; f[7] = __uint_as_float(v[8 * j + 7]) + bb.w;
       if constexpr ((MASK & EPI_SKIP) != 0) {
         if ((flags & EPI_SKIP) && valid) {
-          const uint4 s = sk[j];
+          uint4 s;
+          const uint32_t sa_ = stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(s.x), "=r"(s.y), "=r"(s.z), "=r"(s.w) : "r"(sa_) : "memory");
           const float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
                        d = unpack2<BF16>(s.w);
           f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
@@ -736,12 +760,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-      uint4 ska[4] = {}, skb[4] = {};
+      // skip operands of ALL of this warp's units: issued before waiting for the accumulator, so
+      // their HBM/L2 latency is covered by the MMAs of this very tile
+      constexpr int kMineU = (NTILE == 16) ? 1 : (R * (NTILE / 32)) / 2;
+      uint4 sk[kMineU][4] = {};
       if constexpr (NTILE != 16) {
-        // skip operand of this warp's first unit: in flight while the MMAs of the tile still run
         constexpr int G0 = NTILE / 32;
-        const int uf = half * (R * G0 / 2);
-        skip_prefetch<MASK>(p, tc, tc.y0 + uf / G0, tc.nt * NTILE + (uf % G0) * 32, quad, lane, ska);
+#pragma unroll
+        for (int k = 0; k < kMineU; ++k) {
+          const int u = half * kMineU + k;
+          skip_prefetch<MASK>(p, tc, tc.y0 + u / G0, tc.nt * NTILE + (u % G0) * 32, quad, lane, sk[k]);
+        }
       }
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
@@ -790,26 +819,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (k + 1 < kMine) {
             const int u = u0 + k + 1;
             tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
-            skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
           } else {
             release_acc();
           }
           if (work) {
             const int u = u0 + k;
-            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
+            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, sk[k], bias_s, stg, quad, lane);
           }
           if (k + 1 < kMine) {
             tmem_ld_wait();
             if (k + 2 < kMine) {
               const int u = u0 + k + 2;
               tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
-              skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
             } else {
               release_acc();
             }
             const int u = u0 + k + 1;
             if (work)
-              epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
+              epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, sk[k + 1], bias_s, stg, quad, lane);
           }
         }
       }
