@@ -1,0 +1,46 @@
+"""The callers either side of the hot path, as thin torch glue over the B200 class:
+
+* DenoisingModel.padding_input / crop_output (Experimental_root/models/denoising_model.py:133-168):
+  reflect-pad H and W up to multiples of 4, crop back afterwards;
+* temp_denoise (Experimental_root/models/validation_seq_infer.py:10-31): constant sigma map, forward,
+  clamp to [0,1].
+
+Pad / clamp / crop run as ordinary torch ops on the device (two cheap full-resolution passes over
+3-channel tensors); the concat with the noise map is folded into the first kernel by the C ABI.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def pad_to_multiple_of_4(seq: torch.Tensor):
+    """[F,C,H,W] -> reflect-padded tensor and the (pad_h, pad_w) that were added
+    (denoising_model.py:133-159 pads bottom/right with 'reflect')."""
+    h, w = seq.shape[-2:]
+    ph, pw = (4 - h % 4) % 4, (4 - w % 4) % 4
+    if ph or pw:
+        seq = F.pad(seq, (0, pw, 0, ph), mode="reflect")
+    return seq, (ph, pw)
+
+
+def denoise_sequence(net, noisy: torch.Tensor, sigma: float | torch.Tensor) -> torch.Tensor:
+    """noisy: [F,3,H,W] in [0,1]; sigma: noise std in [0,1] (scalar or [F,1,H,W] constant map).
+    Returns the denoised [F,3,H,W] clamped to [0,1] — what DenoisingModel.test produces for one
+    validation folder (pad -> denoise_seq/temp_denoise -> crop)."""
+    Fr, C, H, W = noisy.shape
+    assert C == 3
+    dev = torch.device("cuda", torch.cuda.current_device()) if not noisy.is_cuda else noisy.device
+    x, (ph, pw) = pad_to_multiple_of_4(noisy.to(dev).float())
+    if torch.is_tensor(sigma):
+        s = float(sigma.flatten()[0])
+        assert abs(float(sigma.float().mean()) - s) < 1e-5     # validation_seq_infer.py:19
+    else:
+        s = float(sigma)
+    nmap = torch.full((Fr, 1, x.shape[-2], x.shape[-1]), s, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        out = net(x[None], noise_map=nmap[None])[0]
+    out = out.clamp(0.0, 1.0)
+    if ph or pw:
+        out = out[..., :H, :W]
+    return out

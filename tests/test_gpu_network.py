@@ -269,3 +269,20 @@ def test_spatial_tiles_bit_exact():
         assert torch.equal(tiling.forward_tiled_local(fwd, xc, 1, 3), full)
         # 4 px less than the receptive field is already visible
         assert not torch.equal(tiling.forward_tiled_local(fwd, xc, 1, 2, halo=76), full)
+
+
+def test_denoise_sequence_pad_clamp_crop_like_the_reference_callers():
+    """pipeline.denoise_sequence == reflect-pad -> forward -> clamp -> crop computed with the
+    oracle (DenoisingModel.test + temp_denoise semantics), on a size that is not a multiple of 4."""
+    import torch.nn.functional as F
+    from bsvd_b200 import pipeline
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(3, 30, 45, seed=50)
+    noisy, sigma = x[:, :3].clamp(0, 1), float(x[0, 3, 0, 0])
+    got = pipeline.denoise_sequence(net, noisy.cuda(), sigma).float().cpu()
+    xp = F.pad(noisy, (0, 3, 0, 2), mode="reflect")
+    ref_in = torch.cat([xp, torch.full((3, 1, 32, 48), sigma)], dim=1)
+    ref = O.forward_clip(layers, ref_in).clamp(0, 1)[..., :30, :45]
+    assert got.shape == (3, 3, 30, 45)
+    assert float((got - ref).abs().max()) <= TOL["fp16"]
+    assert float(got.min()) >= 0.0 and float(got.max()) <= 1.0

@@ -1,0 +1,153 @@
+"""Secondary BASELINE.json configurations (bench.py owns configs[1] / the driver contract):
+
+  python tools/bench_extra.py stream   [--frames 100] [--precision bf16]     # configs[2]
+  torchrun ... tools/bench_extra.py tiles --rows 4 --cols 2                   # configs[4] (world = rows*cols)
+
+Each prints one JSON line (rank 0).  CUDA-event timing, max over ranks for multi-GPU."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bsvd_b200.arch import BSVD  # noqa: E402
+from bsvd_b200 import tiling  # noqa: E402
+from oracle import bsvd_oracle as O  # noqa: E402
+
+
+def make_net(prec, dev):
+    net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+               act='relu6', pretrain_ckpt=None, precision=prec)
+    net.load_tsn_state(O.make_synthetic_params(0, 0.5))
+    return net.to(dev).eval()
+
+
+def stream(args):
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    net = make_net(args.precision, dev)
+    H, W, F = 540, 960, args.frames
+    x, _ = O.make_synthetic_clip(min(F, 20), H, W, seed=1)
+    frames = [x[i % x.shape[0]:i % x.shape[0] + 1].to(dev) for i in range(F)]
+
+    def run():
+        net.reset()
+        outs = 0
+        for f in frames:
+            if net.feedin_one_element(f) is not None:
+                outs += 1
+        while outs < F:
+            if net.feedin_one_element(None) is not None:
+                outs += 1
+        net.reset()
+        return outs
+
+    with torch.no_grad():
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # parity of the streaming schedule on a short prefix (fp32 oracle, CPU)
+    xs = x[:3]
+    with torch.no_grad():
+        net.reset()
+        outs = [net.feedin_one_element(xs[i:i + 1].to(dev)) for i in range(3)]
+        while sum(o is not None for o in outs) < 3:
+            outs.append(net.feedin_one_element(None))
+        net.reset()
+    y = torch.cat([o for o in outs if o is not None]).float().cpu()
+    ref = O.forward_clip(O.layers_from_tsn_state(O.make_synthetic_params(0, 0.5)), xs)
+    print(json.dumps({
+        "metric": "denoised frames/sec at 540x960 (c=64)", "value": F / (ms / 1e3), "unit": "frames/s",
+        "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
+        "config": {"workload": f"BSVD-64 streaming bidirectional-buffer mode, {F}-frame 540x960 "
+                               f"sequence, {args.precision} (BASELINE.json configs[2]); one "
+                               "feedin_one_element call per frame + 16 drain calls",
+                   "latency_frames": 16},
+        "parity": {"max_abs": float((y - ref).abs().max()),
+                   "tolerance": 1e-2 if args.precision == "bf16" else 1e-3},
+        "workspace_bytes": None}), flush=True)
+
+
+def tiles(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    assert world == args.rows * args.cols, "world size must equal rows*cols"
+    dist.init_process_group("nccl", device_id=dev)
+    net = make_net(args.precision, dev)
+    T, H, W = args.frames, args.height, args.width
+    plan = tiling.tile_plan(H, W, args.rows, args.cols)
+    t = plan[rank]
+    # every rank synthesises the same frame and keeps only its own tile (stands for a decoder that
+    # delivers tiles); the 80-px ring then comes from the neighbours through the all_gather
+    x, _ = O.make_synthetic_clip(T, H, W, seed=1)
+    x_tile = x[:, :, t.y0:t.y1, t.x0:t.x1].contiguous().to(dev)
+    fwd = lambda r: net(r[None])[0]  # noqa: E731
+
+    def step():
+        with torch.no_grad():
+            return tiling.forward_tiled_distributed(fwd, x_tile, H, W, args.rows, args.cols)
+
+    for _ in range(2):
+        full = step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        full = step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    exact = None
+    if args.check and rank == 0:
+        with torch.no_grad():
+            whole = net(x[None].to(dev))[0]
+        exact = bool(torch.equal(whole, full))
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"denoised frames/sec at {H}x{W} (c=64)", "value": T / (float(ms) / 1e3),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "ms_per_step": float(ms),
+            "scaling": "strong", "dtype": args.precision,
+            "config": {"workload": f"BSVD-64 {H}x{W} {T}-frame clip, {args.rows}x{args.cols} spatial "
+                                   f"tiles, one per GPU, {tiling.HALO}-px input ring exchanged by NCCL "
+                                   "all_gather over NVLink, outputs all_gathered "
+                                   "(BASELINE.json configs[4], bit-exact variant)"},
+            "bit_exact_vs_single_gpu": exact}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["stream", "tiles"])
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--precision", default=None)
+    ap.add_argument("--rows", type=int, default=4)
+    ap.add_argument("--cols", type=int, default=2)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    if a.mode == "stream":
+        a.frames = a.frames or 100
+        a.precision = a.precision or "bf16"
+        stream(a)
+    else:
+        a.frames = a.frames or 10
+        a.precision = a.precision or "fp16"
+        tiles(a)
