@@ -267,11 +267,13 @@ struct StageLaunch {
 
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
-  static bool attr_done = false;
+  static bool attr_done[64] = {};      // per device: the attribute is per (function, device)
   auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK>;
-  if (!attr_done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
-    attr_done = true;
+    attr_done[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -279,12 +281,17 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL, see conv_tc.cuh
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   if (CTA2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  cfg.attrs = attr; cfg.numAttrs = na;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.p));
   return 0;
 }
@@ -437,15 +444,24 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
 
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
   if (L.ntile == 16) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
       CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
       CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
-      attr_done = true;
+      attr_done[dev & 63] = true;
     }
-    if (L.p.flags & EPI_BF16) final_conv_kernel<true><<<L.grid, kThreads, L.smem, st>>>(L.map, L.p);
-    else final_conv_kernel<false><<<L.grid, kThreads, L.smem, st>>>(L.map, L.p);
-    CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (L.p.flags & EPI_BF16) CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<true>, L.map, L.p));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<false>, L.map, L.p));
     return 0;
   }
   if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L, st);

@@ -48,7 +48,7 @@ enum : int {
   EPI_SKIP = 4,
   EPI_SHIFT = 8,
   EPI_RESID_IN = 16,    // temp1 outc.3: out[:, :3] = raw_in[:, :3] - out[:, :3]
-  EPI_FINAL = 32,       // temp2 outc.3: fp32 NCHW out = skip[:, :3] - conv[:, :3]
+  EPI_FINAL = 32,       // temp2 outc.3 (final_conv.cuh): fp32 NCHW out = skip[:, :3] - conv[:, :3]
   EPI_BF16 = 64,        // 16-bit storage type is bf16 (else fp16)
   EPI_ZERO_FUTURE = 128 // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
 };
@@ -196,16 +196,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
 // ---- CTA-pair (cta_group::2) variants: both CTAs issue their own TMA loads but signal the LEADER
 // CTA's mbarrier (peer bit 24 of the shared::cluster address cleared); the leader issues one MMA
 // that drives both SMs' tensor cores and multicasts the commit to both CTAs' barriers.
@@ -266,6 +256,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank)
       : "memory");
+}
+// Programmatic dependent launch: let the next stage's CTAs start their prologue (barrier init, TMEM
+// allocation, bias staging) on SMs this grid has already left; `pdl_wait` then blocks until the
+// previous stage has completed and its stores are visible.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
@@ -551,8 +550,7 @@ template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ ConvParams p) {
-  static_assert(NTILE == 16 || NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
-  static_assert(!(CTA2 && NTILE == 16), "the 3-channel output stage stays single-CTA");
+  static_assert(NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
   constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator buffer
   constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
@@ -611,6 +609,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();            // everything above touched only weights/bias; activations come next
 
   const int ntaps = p.tap_end - p.tap_begin;
   // bytes one stage receives in total (both CTAs of a pair signal the leader's barrier)
@@ -762,9 +762,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       // skip operands of ALL of this warp's units: issued before waiting for the accumulator, so
       // their HBM/L2 latency is covered by the MMAs of this very tile
-      constexpr int kMineU = (NTILE == 16) ? 1 : (R * (NTILE / 32)) / 2;
+      constexpr int kMineU = (R * (NTILE / 32)) / 2;
       uint4 sk[kMineU][4] = {};
-      if constexpr (NTILE != 16) {
+      {
         constexpr int G0 = NTILE / 32;
 #pragma unroll
         for (int k = 0; k < kMineU; ++k) {
@@ -784,26 +784,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       };
       const bool live = tc.t < p.T;            // false only for the padding tile of an odd pair
-      if constexpr (NTILE == 16) {
-        // temp2 outc.3 + residual (bsvd_arch.py:394, 408-414): fp32 NCHW out = temp1_out[:, :3] - conv[:, :3]
-        const int r = half;                    // R == 2: one row per warp half
-        uint32_t v[32];
-        tmem_ld16(tacc + r * NTILE, v);
-        tmem_ld_wait();
-        release_acc();
-        const int x = tc.x0 + quad * 32 + lane, y = tc.y0 + r;
-        if (live && x < p.W && y < p.H) {
-          const long long plane = static_cast<long long>(p.H) * p.W;
-          const long long pix = static_cast<long long>(y) * p.W + x;
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane + pix;
-          const uint2 s = __ldg(reinterpret_cast<const uint2*>(
-              reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride + pix * p.skip_C));
-          const float2 s01 = unpack2<BF16>(s.x), s23 = unpack2<BF16>(s.y);
-          o[0] = s01.x - (__uint_as_float(v[0]) + bias_s[0]);
-          o[plane] = s01.y - (__uint_as_float(v[1]) + bias_s[1]);
-          o[2 * plane] = s23.x - (__uint_as_float(v[2]) + bias_s[2]);
-        }
-      } else {
+      {
         constexpr int G = NTILE / 32;          // 32-column groups per row
         constexpr int kUnits = R * G;
         constexpr int kMine = kUnits / 2;

@@ -68,6 +68,8 @@ final_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
