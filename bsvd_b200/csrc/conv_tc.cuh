@@ -70,7 +70,8 @@ struct ConvParams {
   uint32_t a_tx_bytes;                     // bytes one A-stage TMA box delivers
   int w_resident;
   int desc_variant;     // 0 production; debug bits: 2 skip MMA issue, 4 skip epilogue stores,
-                        // 8 tap offsets forced to 0 (aligned A), 16 no TMA loads at all
+                        // 8 tap offsets forced to 0 (aligned A), 16 no TMA loads at all,
+                        // 64 no skip loads, 128 no global stores
   // ---- operands ----
   const void* wpack;    // [n_tile][chunk][tap][NTILE][64] 16-bit, rows pre-swizzled (SW128)
   const float* bias;    // [GEMM N]
@@ -106,7 +107,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  // relaxed (see mbar_arrive_cluster): no memory fence wanted on the accumulator hand-back
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
@@ -248,12 +250,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       ::"r"(bar), "h"(static_cast<uint16_t>(3))
       : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// Arrive on the barrier at the same offset in CTA `rank` of the cluster.  RELAXED on purpose: the
+// only thing this arrival publishes is "my tcgen05.ld of the accumulator has completed", which
+// tcgen05.fence::before_thread_sync orders.  A .release arrive makes ptxas emit MEMBAR.ALL.GPU +
+// ERRBAR, i.e. the warp would first wait for every global store of its previous units to drain
+// (measured: 20 % of all stall samples, and the whole epilogue store/skip traffic serialised
+// behind the MMAs).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank)
       : "memory");
 }
@@ -378,7 +385,7 @@ __device__ __forceinline__ void skip_prefetch(const ConvParams& p, const TileCoo
   // Coalesced layout (same as the store phase): lane = (pixel group lane>>2, 16-byte chunk lane&3),
   // so four lanes fetch the 64 contiguous bytes of one pixel: full sectors, 8 lines per request.
   if constexpr ((MASK & EPI_SKIP) != 0) {
-    if ((p.flags & EPI_SKIP) && tc.t < p.T && y < p.H) {
+    if ((p.flags & EPI_SKIP) && tc.t < p.T && y < p.H && !(p.desc_variant & 64)) {
       const int j = lane & 3;
       const int n0 = nbase + 8 * j;
       int c0 = n0, q = 0;
@@ -424,10 +431,26 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
     }
   }
   // ------------------------------ phase 1 ------------------------------
+  // (shared-memory accesses are batched: all loads of a phase are issued before their first use)
   {
     const int x = tc.x0 + quad * 32 + lane;
     const bool valid = (x < p.W) && (y < p.H);
     const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase);
+    const uint32_t row = stg + lane * 64;
+    const uint32_t swz = (lane >> 1) & 3;
+    uint4 sv[4];
+    bool add_skip = false;
+    if constexpr ((MASK & EPI_SKIP) != 0) {
+      add_skip = (flags & EPI_SKIP) && valid;
+      if (flags & EPI_SKIP) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(sv[j].x), "=r"(sv[j].y), "=r"(sv[j].z), "=r"(sv[j].w)
+                       : "r"(row + ((j ^ swz) << 4)) : "memory");
+      }
+    }
+    uint4 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float f[8];
@@ -437,13 +460,9 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
       f[4] = __uint_as_float(v[8 * j + 4]) + bb.x; f[5] = __uint_as_float(v[8 * j + 5]) + bb.y;
       f[6] = __uint_as_float(v[8 * j + 6]) + bb.z; f[7] = __uint_as_float(v[8 * j + 7]) + bb.w;
       if constexpr ((MASK & EPI_SKIP) != 0) {
-        if ((flags & EPI_SKIP) && valid) {
-          uint4 s;
-          const uint32_t sa_ = stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(s.x), "=r"(s.y), "=r"(s.z), "=r"(s.w) : "r"(sa_) : "memory");
-          const float2 a = unpack2<BF16>(s.x), b = unpack2<BF16>(s.y), c = unpack2<BF16>(s.z),
-                       d = unpack2<BF16>(s.w);
+        if (add_skip) {
+          const float2 a = unpack2<BF16>(sv[j].x), b = unpack2<BF16>(sv[j].y),
+                       c = unpack2<BF16>(sv[j].z), d = unpack2<BF16>(sv[j].w);
           f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
           f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
         }
@@ -458,23 +477,23 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
           for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
         }
       }
-      uint4 o;
-      o.x = pack2<BF16>(f[0], f[1]); o.y = pack2<BF16>(f[2], f[3]);
-      o.z = pack2<BF16>(f[4], f[5]); o.w = pack2<BF16>(f[6], f[7]);
+      o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
+      o[j].z = pack2<BF16>(f[4], f[5]); o[j].w = pack2<BF16>(f[6], f[7]);
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
         if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid && p.aux_out) {
           const long long pix = (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
-          reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o.x, o.y);
+          reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o[j].x, o[j].y);
         }
       }
       if (flags & EPI_RELU6) {
-        o.x = relu6_packed<BF16>(o.x); o.y = relu6_packed<BF16>(o.y);
-        o.z = relu6_packed<BF16>(o.z); o.w = relu6_packed<BF16>(o.w);
+        o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
+        o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
       }
-      const uint32_t a = stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
-                   "r"(o.z), "r"(o.w) : "memory");
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ swz) << 4)),
+                   "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w) : "memory");
   }
   __syncwarp();
   // ------------------------------ phase 2 ------------------------------
@@ -523,17 +542,20 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
     const long long off0 = (static_cast<long long>(oy) * p.out_W + ox0) * p.out_C + c0;
     const int step = (ps ? 16 : 8) * p.out_C;
     const bool row_ok = y < p.H;
-    uint32_t a0 = stg + (lane >> 2) * 64;
+    const uint32_t a0 = stg + (lane >> 2) * 64;
+    uint4 o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pl = 8 * i + (lane >> 2);
-      const uint32_t a = a0 + i * 512 + ((j ^ ((pl >> 1) & 3)) << 4);
-      uint4 o;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(a) : "memory");
-      if (row_ok && xl + 8 * i < p.W) {
+                   : "=r"(o[i].x), "=r"(o[i].y), "=r"(o[i].z), "=r"(o[i].w)
+                   : "r"(a0 + i * 512 + ((j ^ ((pl >> 1) & 3)) << 4)) : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (row_ok && xl + 8 * i < p.W && !(p.desc_variant & 128)) {
         const long long off = off0 + static_cast<long long>(i) * step;
-        if (dst) *reinterpret_cast<uint4*>(dst + off) = o;
+        if (dst) *reinterpret_cast<uint4*>(dst + off) = o[i];
         if constexpr ((MASK & EPI_SHIFT) != 0) {
           if (zdst) *reinterpret_cast<uint4*>(zdst + off) = make_uint4(0, 0, 0, 0);
         }
@@ -760,18 +782,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
-      // skip operands of ALL of this warp's units: issued before waiting for the accumulator, so
-      // their HBM/L2 latency is covered by the MMAs of this very tile
-      constexpr int kMineU = (R * (NTILE / 32)) / 2;
-      uint4 sk[kMineU][4] = {};
-      {
-        constexpr int G0 = NTILE / 32;
-#pragma unroll
-        for (int k = 0; k < kMineU; ++k) {
-          const int u = half * kMineU + k;
-          skip_prefetch<MASK>(p, tc, tc.y0 + u / G0, tc.nt * NTILE + (u % G0) * 32, quad, lane, sk[k]);
-        }
-      }
+      constexpr int G = NTILE / 32;            // 32-column groups per row
+      constexpr int kUnits = R * G;
+      constexpr int kMine = kUnits / 2;
+      static_assert(kMine % 2 == 0, "each warp half handles an even number of units");
+      const int u0 = half * kMine;
+      const int nb0 = tc.nt * NTILE;           // global GEMM column of this tile's first column
+      // skip operand of the first unit: issued before waiting for the accumulator, so its latency
+      // is covered by the MMAs of this very tile; later units are prefetched one unit ahead
+      uint4 ska[4] = {}, skb[4] = {};
+      skip_prefetch<MASK>(p, tc, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
@@ -784,41 +804,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       };
       const bool live = tc.t < p.T;            // false only for the padding tile of an odd pair
-      {
-        constexpr int G = NTILE / 32;          // 32-column groups per row
-        constexpr int kUnits = R * G;
-        constexpr int kMine = kUnits / 2;
-        static_assert(kUnits % 2 == 0, "units must split evenly over the two warp halves");
-        const int u0 = half * kMine;
-        const int nb0 = tc.nt * NTILE;         // global GEMM column of this tile's first column
-        const bool work = live && !(p.desc_variant & 4);
-        uint32_t va[32], vb[32];
-        tmem_ld32(tacc + (u0 / G) * NTILE + (u0 % G) * 32, va);
-#pragma unroll
-        for (int k = 0; k < kMine; k += 2) {
-          tmem_ld_wait();
-          if (k + 1 < kMine) {
-            const int u = u0 + k + 1;
-            tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
-          } else {
-            release_acc();
-          }
-          if (work) {
-            const int u = u0 + k;
-            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, sk[k], bias_s, stg, quad, lane);
-          }
-          if (k + 1 < kMine) {
-            tmem_ld_wait();
-            if (k + 2 < kMine) {
-              const int u = u0 + k + 2;
-              tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
-            } else {
-              release_acc();
-            }
-            const int u = u0 + k + 1;
-            if (work)
-              epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, sk[k + 1], bias_s, stg, quad, lane);
-          }
+      const bool work = live && !(p.desc_variant & 4);
+      uint32_t va[32], vb[32];
+      tmem_ld32(tacc + (u0 / G) * NTILE + (u0 % G) * 32, va);
+      // two units per iteration (register double buffering); NOT unrolled further: the epilogue
+      // body is large and the three warp roles already compete for the instruction cache
+#pragma unroll 1
+      for (int k = 0; k < kMine; k += 2) {
+        tmem_ld_wait();
+        {
+          const int u = u0 + k + 1;
+          tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
+          skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
+        }
+        if (work) {
+          const int u = u0 + k;
+          epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
+        }
+        tmem_ld_wait();
+        if (k + 2 < kMine) {
+          const int u = u0 + k + 2;
+          tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
+          skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
+        } else {
+          release_acc();
+        }
+        if (work) {
+          const int u = u0 + k + 1;
+          epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
         }
       }
     }

@@ -22,9 +22,11 @@ def run(name, T, H, W, cin, cout, flags, variant=0, a_stages=0, reps=4, w_stages
     by = 2.0 * T * (H * W * cin + Ho * Wo * Co * (2 if flags & K else 1))
     print(f"{name:34s} var={variant} a_st={a_stages} w_st={w_stages}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TF/s  {by/ms/1e6:7.1f} GB/s", flush=True)
 T = 10
-for var in (0, 4):
-    for (a, w) in ((0, 0), (2, 2), (2, 3), (2, 4), (2, 6), (3, 2), (3, 3), (1, 6), (1, 8)):
-        run("256->256 quarter shift", T, 135, 240, 256, 256, R | S, var, a, 4, w)
-for var in (0, 4):
-    for (a, w) in ((0, 0), (2, 2), (2, 4), (2, 7), (1, 8), (1, 12)):
-        run("128->128 half shift", T, 270, 480, 128, 128, R | S, var, a, 4, w)
+V = (0, 4)
+for var in V: run("64->64 full", T, 540, 960, 64, 64, R, var)
+for var in V: run("128->128 half shift", T, 270, 480, 128, 128, R | S, var)
+for var in V: run("256->256 quarter shift", T, 135, 240, 256, 256, R | S, var)
+for var in V: run("64->128 s2", T, 540, 960, 64, 128, R | D | S, var)
+for var in V: run("128->256 ps skip (upc1.conv)", T, 270, 480, 128, 256, P | K, var)
+for var in V: run("256->512 ps skip shift", T, 135, 240, 256, 512, P | K | S, var)
+for var in V: run("128->256 s2", T, 270, 480, 128, 256, R | D | S, var)
