@@ -250,10 +250,10 @@ struct StageIO {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // dynamic shared memory: 227 KB opt-in limit minus the kernel's static shared (barriers, bias)
 constexpr size_t kSmemOptIn = 232448 - 3072;
-constexpr size_t kStagingBytes = 8 * kStageBytesPerWarp;   // epilogue staging of the 8 epilogue warps
+static size_t staging_bytes(int ew) { return (size_t)ew * kStageBytesPerWarp; }   // epilogue staging
 
 struct StageLaunch;
-template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st);
 struct StageLaunch {
   CUtensorMap map;      // activations
@@ -263,12 +263,13 @@ struct StageLaunch {
   size_t smem = 0;
   int ntile = 0, rows = 0;
   int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
+  int ew = 8;           // epilogue warps (8 or 16)
 };
 
-template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   static bool attr_done[64] = {};      // per device: the attribute is per (function, device)
-  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK>;
+  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK, EW>;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
@@ -278,7 +279,7 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(64 + 32 * EW);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -303,14 +304,14 @@ constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
 constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
+  if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
+  const int f = L.p.flags & kMaskAll;
   {
-    if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll>(L, st);
-    const int f = L.p.flags & kMaskAll;
-    if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain>(L, st);
-    if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift>(L, st);
-    if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid>(L, st);
-    return launch_inst<NTILE, R, BF16, true, kMaskAll>(L, st);
+    if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
+    if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
+    if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
   }
+  return launch_inst<NTILE, R, BF16, true, kMaskAll, 8>(L, st);
 }
 template <int NTILE, int R>
 static int launch_one(const StageLaunch& L, cudaStream_t st) {
@@ -348,6 +349,10 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   // of the filter slab.  The 3-channel output stage (N=16) stays single-CTA.
   const int cta2 = (s.ntile != 16 && use_cta2_default() && !(desc_variant & 32)) ? 1 : 0;
   L->cta2 = cta2;
+  // 8 epilogue warps: 16 were measured (kernel template parameter EW) and bring nothing — the
+  // gap between a full stage and its epilogue-less run is shared-memory/L2 contention, not latency
+  L->ew = 8;
+  const size_t kStagingBytes = staging_bytes(L->ew);
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;

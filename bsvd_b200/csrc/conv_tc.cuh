@@ -568,8 +568,8 @@ __device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoo
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int NTILE, int R, bool BF16, bool CTA2, int MASK>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
@@ -611,11 +611,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), CTA2 ? 2 * (kEpiThreads / 32) : (kEpiThreads / 32));   // one arrival per epilogue warp
+      mbar_init(acc_empty(b), CTA2 ? 2 * EW : EW);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_tiles * NTILE; i += kThreads) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_tiles * NTILE; i += 64 + 32 * EW) bias_s[i] = p.bias[i];
   if (warp == 1) {
     if constexpr (CTA2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -775,7 +775,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ======================================= epilogue =======================================
     const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                  // two warps share a quadrant and split the units
+    const int half = ew >> 2;                  // EW/4 warps share a TMEM lane quadrant and split the units
     const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t it = 0;
@@ -784,8 +784,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       constexpr int G = NTILE / 32;            // 32-column groups per row
       constexpr int kUnits = R * G;
-      constexpr int kMine = kUnits / 2;
-      static_assert(kMine % 2 == 0, "each warp half handles an even number of units");
+      static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+      constexpr int kMine = kUnits / (EW / 4);
+      static_assert(kMine >= 1 && kMine * (EW / 4) == kUnits, "units must split evenly over the warps of a quadrant");
       const int u0 = half * kMine;
       const int nb0 = tc.nt * NTILE;           // global GEMM column of this tile's first column
       // skip operand of the first unit: issued before waiting for the accumulator, so its latency
@@ -812,26 +813,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll 1
       for (int k = 0; k < kMine; k += 2) {
         tmem_ld_wait();
-        {
+        if (k + 1 < kMine) {
           const int u = u0 + k + 1;
           tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
           skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
+        } else {
+          release_acc();
         }
         if (work) {
           const int u = u0 + k;
           epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
         }
-        tmem_ld_wait();
-        if (k + 2 < kMine) {
-          const int u = u0 + k + 2;
-          tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
-          skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
-        } else {
-          release_acc();
-        }
-        if (work) {
-          const int u = u0 + k + 1;
-          epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
+        if (k + 1 < kMine) {
+          tmem_ld_wait();
+          if (k + 2 < kMine) {
+            const int u = u0 + k + 2;
+            tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
+            skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
+          } else {
+            release_acc();
+          }
+          if (work) {
+            const int u = u0 + k + 1;
+            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
+          }
         }
       }
     }
