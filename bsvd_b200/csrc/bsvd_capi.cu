@@ -153,7 +153,8 @@ struct StageSpec {
     gemm_n = final_out ? 16 : cout;
     static const int ntile_max = [] { const char* e = getenv("BSVD_B200_NTILE_MAX"); return e ? atoi(e) : 256; }();
     ntile = gemm_n >= 256 ? (ntile_max >= 256 ? 256 : 128) : gemm_n;
-    rows = final_out ? kFinalR : ((ntile == 256) ? 1 : 2);
+    static const int r256 = [] { const char* e = getenv("BSVD_B200_R256"); return e ? atoi(e) : 1; }();
+    rows = final_out ? kFinalR : ((ntile == 256) ? r256 : 2);
     cin_chunks = first_im2col ? 1 : cin / kChunk;
     tap_begin = first_im2col ? 4 : 0;
     tap_end = first_im2col ? 5 : 9;
@@ -472,6 +473,7 @@ static int launch_stage(const StageLaunch& L, cudaStream_t st) {
   if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L, st);
   if (L.ntile == 128 && L.rows == 2) return launch_one<128, 2>(L, st);
   if (L.ntile == 256 && L.rows == 1) return launch_one<256, 1>(L, st);
+  if (L.ntile == 256 && L.rows == 2) return launch_one<256, 2>(L, st);
   return fail("no kernel instance for NTILE=%d R=%d", L.ntile, L.rows);
 }
 
@@ -498,43 +500,58 @@ static void free_stage(StageDev& sd) {
 // Patch layout per pixel: k = tap*4 + c for tap<9, c<4 ; k in [36,64) = 0.
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void prep_patches_kernel(const float* __restrict__ in, const float* __restrict__ nmap,
-                                    uint16_t* __restrict__ out, int T, int in_c, int H, int W) {
-  const long long total = (long long)T * H * W;
+__global__ void __launch_bounds__(256)
+prep_patches_kernel(const float* __restrict__ in, const float* __restrict__ nmap,
+                    uint16_t* __restrict__ out, int T, int in_c, int H, int W) {
+  // Phase 1: thread = pixel (coalesced fp32 plane reads along x), builds the 36-value patch and parks
+  // its 128-byte row in shared memory (16-byte chunks XOR-swizzled by the pixel index).
+  // Phase 2: thread = 16-byte chunk: the block writes its 256 pixels x 128 B fully coalesced.
+  __shared__ uint4 tile[256 * 8];
+  const long long npix = (long long)T * H * W;
   const long long plane = (long long)H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int t = (int)(i / plane);
-    float v[36];
+  for (long long base = (long long)blockIdx.x * 256; base < npix; base += (long long)gridDim.x * 256) {
+    const long long i = base + threadIdx.x;
+    if (i < npix) {
+      const int x = (int)(i % W);
+      const int y = (int)((i / W) % H);
+      const int t = (int)(i / plane);
+      float v[40];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      const bool ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+      for (int k = 36; k < 40; ++k) v[k] = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float f = 0.f;
-        if (ok) {
-          if (c < in_c) f = __ldg(in + ((long long)t * in_c + c) * plane + (long long)yy * W + xx);
-          else if (nmap) f = __ldg(nmap + (long long)t * plane + (long long)yy * W + xx);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        const bool ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float f = 0.f;
+          if (ok) {
+            if (c < in_c) f = __ldg(in + ((long long)t * in_c + c) * plane + (long long)yy * W + xx);
+            else if (nmap) f = __ldg(nmap + (long long)t * plane + (long long)yy * W + xx);
+          }
+          v[tap * 4 + c] = f;
         }
-        v[tap * 4 + c] = f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (j < 5) {
+          u.x = pack2<BF16>(v[8 * j + 0], v[8 * j + 1]); u.y = pack2<BF16>(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack2<BF16>(v[8 * j + 4], v[8 * j + 5]); u.w = pack2<BF16>(v[8 * j + 6], v[8 * j + 7]);
+        }
+        tile[threadIdx.x * 8 + (j ^ (threadIdx.x & 7))] = u;
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(out) + base * 8;
+    const long long lim = (npix - base < 256 ? npix - base : 256) * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (j * 8 < 36) {
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = (j * 8 + k < 36) ? v[j * 8 + k] : 0.f;
-        u.x = pack2<BF16>(f[0], f[1]); u.y = pack2<BF16>(f[2], f[3]);
-        u.z = pack2<BF16>(f[4], f[5]); u.w = pack2<BF16>(f[6], f[7]);
-      }
-      o[j] = u;
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * 256 + threadIdx.x;        // chunk index inside the block's 32 KB
+      const int px = e >> 3, j = e & 7;
+      if (e < lim) o[e] = tile[px * 8 + (j ^ (px & 7))];
     }
+    __syncthreads();
   }
 }
 
@@ -853,7 +870,7 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
     CUDA_TRY(cudaEventRecord((*evs)[0], st));
   }
   const long long npix = (long long)T * H * W;
-  const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
+  const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 8);
   if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
   else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
   CUDA_TRY(cudaGetLastError());
@@ -1043,7 +1060,7 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
       CUDA_TRY(cudaMemcpyAsync(slot + 3 * plane, noise_map, plane * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
     const long long npix = (long long)plane;
-    const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 16);
+    const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 8);
     uint16_t* P = reinterpret_cast<uint16_t*>(S.ring[0][kRingP]);
     if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);
     else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);

@@ -573,8 +573,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
-  constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator buffer
-  constexpr int kTmemCols = (2 * kAccCols < 32) ? 32 : 2 * kAccCols;
+  constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator set
+  // two accumulator sets (epilogue of tile i overlaps the MMAs of tile i+1) when they fit in the
+  // 512 TMEM columns, otherwise one set (bigger tile: every filter slab is reused for R rows)
+  constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;
+  constexpr int kTmemCols = (kNumAcc * kAccCols < 32) ? 32 : kNumAcc * kAccCols;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
@@ -709,7 +712,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       uint32_t it = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
-        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
+      const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(acc_empty(buf), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kAccCols;
@@ -781,7 +785,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t it = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
-      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
+      const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
       constexpr int G = NTILE / 32;            // 32-column groups per row
       constexpr int kUnits = R * G;
       static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
