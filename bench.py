@@ -275,7 +275,8 @@ def run_b200(args):
             el += co.value * (npx / res_div)
         if l == 15:
             el += 3 * npx
-        name = f"conv3x3_tc_kernel<{nt.value},{rw.value}>"
+        name = ("first_conv_kernel" if s == 1 else "final_conv_kernel" if s == 32
+                else f"conv3x3_tc_kernel<{nt.value},{rw.value}>")
         k = kernels.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         k["ms"] += stage_ms[s] / max(passes.value, 1)
         k["flops"] += fl * T_CLIP
@@ -312,8 +313,6 @@ def run_b200(args):
     per_kernel = {n: {"ms_per_step": k["ms"], "tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12,
                       "hbm_gbs": k["bytes"] / (k["ms"] * 1e-3) / 1e9, "launches": k["launches"]}
                   for n, k in kernels.items()}
-    per_kernel["prep_patches_kernel"] = {"ms_per_step": stage_ms[0] / max(passes.value, 1),
-                                         "launches": 1}
 
     # ---- parity check of the timed configuration against the fp32 oracle (bounded sample)
     from oracle import bsvd_oracle as O2

@@ -77,12 +77,14 @@ class BSVD(nn.Module):
         super().__init__()
         chns = list(chns)
         if not (chns == [64, 128, 256] and mid_ch == 64 and interm_ch == 64 and in_ch == 4 and
-                out_ch == 3 and norm == 'none' and act == 'relu6' and not shift_input
-                and not blind):
+                out_ch == 3 and norm == 'none' and act == 'relu6' and not shift_input):
             raise NotImplementedError(
                 "bsvd_b200 implements the BSVD-64 configuration of options/test/bsvd_c64.yml only "
                 "(chns=[64,128,256], mid_ch=64, interm_ch=64, norm='none', act='relu6', "
-                "shift_input=False, blind=False); there is no CPU/PyTorch fallback")
+                "shift_input=False; blind=True is supported); there is no CPU/PyTorch fallback")
+        if blind:
+            in_ch = 3      # InputCvBlock(blind=True) drops the noise-map channel (bsvd_arch.py:204-205)
+        self.blind = bool(blind)
         self.cfg = dict(chns=chns, mid_ch=mid_ch, in_ch=in_ch, out_ch=out_ch, interm_ch=interm_ch)
         self.temp1 = _Node()
         self.temp2 = _Node()

@@ -18,6 +18,7 @@
 #include "../../include/bsvd_b200.h"
 #include "conv_tc.cuh"
 #include "final_conv.cuh"
+#include "first_conv.cuh"
 
 namespace bsvd {
 
@@ -211,9 +212,10 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
           for (int k = 0; k < kChunk; ++k) {
             float v = 0.f;
             if (s.first_im2col) {
-              // K index = tap'*cin + ci  (prep kernel writes the 3x3xCin patch per pixel)
-              const int tp = k / s.cin, ci = k % s.cin;
-              if (tp < 9) v = w[((size_t)co * s.cin + ci) * 9 + tp];
+              // K index = tap'*4 + ci: first_conv.cuh builds 4 slots per tap (slot 3 is the noise
+              // map, or zero for the blind 3-channel variant)
+              const int tp = k / 4, ci = k % 4;
+              if (tp < 9 && ci < s.cin) v = w[((size_t)co * s.cin + ci) * 9 + tp];
             } else {
               const int ci = c * kChunk + k;
               v = w[((size_t)co * s.cin + ci) * 9 + tap];
@@ -265,6 +267,10 @@ struct StageLaunch {
   int ntile = 0, rows = 0;
   int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
   int ew = 8;           // epilogue warps (8 or 16)
+  // fused first stage (first_conv.cuh): raw network input, patched per call
+  const float* first_in = nullptr;
+  const float* first_nmap = nullptr;
+  int first_inc = 4;
 };
 
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
@@ -362,6 +368,23 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
   p.xblocks = (Wo + kRunPx - 1) / kRunPx;
   p.yblocks = (Ho + s.rows - 1) / s.rows;
+  if (s.first_im2col) {
+    // dedicated kernel (first_conv.cuh): patches are built in shared memory from the raw input
+    p.n_tiles = 1;
+    p.yblocks = (Ho + kFirstR - 1) / kFirstR;
+    p.positions = p.T * p.yblocks * p.xblocks;
+    p.total_tiles = p.positions;
+    p.wpack = sd.wpack; p.bias = sd.bias;
+    p.flags = EPI_RELU6 | (bf16 ? EPI_BF16 : 0);
+    p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo;
+    p.out_frame_stride = (long long)Ho * Wo * s.cout;
+    L->cta2 = 0;
+    L->map_w = L->map;
+    L->grid = std::min(p.total_tiles, num_sms());
+    L->smem = kFirstSmem;
+    L->ntile = -1; L->rows = kFirstR;
+    return 0;
+  }
   if (s.final_out) {
     // dedicated kernel (final_conv.cuh): tiles of 4 output rows, filter bank resident
     p.n_tiles = 1;
@@ -448,7 +471,33 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   return 0;
 }
 
+static int launch_first(const StageLaunch& L, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    attr_done[dev & 63] = true;
+  }
+  if (!L.first_in) return fail("first stage launched without an input pointer");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(kFirstThreads);
+  cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (L.p.flags & EPI_BF16)
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true>, L.first_in, L.first_nmap, L.first_inc, L.p));
+  else
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false>, L.first_in, L.first_nmap, L.first_inc, L.p));
+  return 0;
+}
+
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
+  if (L.ntile == -1) return launch_first(L, st);
   if (L.ntile == 16) {
     static bool attr_done[64] = {};
     int dev = 0;
@@ -492,67 +541,6 @@ static void free_stage(StageDev& sd) {
   if (sd.wpack) cudaFree(sd.wpack);
   if (sd.bias) cudaFree(sd.bias);
   sd.wpack = nullptr; sd.bias = nullptr; sd.loaded = false;
-}
-
-// ------------------------------------------------------------------------------------------------
-// input staging: fp32 NCHW (+ optional noise map) -> 16-bit NHWC 3x3 patches for inc.convblock.0
-// (the torch.cat of bsvd_arch.py:492-493 and the zero padding of the first conv are folded in).
-// Patch layout per pixel: k = tap*4 + c for tap<9, c<4 ; k in [36,64) = 0.
-// ------------------------------------------------------------------------------------------------
-template <bool BF16>
-__global__ void __launch_bounds__(256)
-prep_patches_kernel(const float* __restrict__ in, const float* __restrict__ nmap,
-                    uint16_t* __restrict__ out, int T, int in_c, int H, int W) {
-  // Phase 1: thread = pixel (coalesced fp32 plane reads along x), builds the 36-value patch and parks
-  // its 128-byte row in shared memory (16-byte chunks XOR-swizzled by the pixel index).
-  // Phase 2: thread = 16-byte chunk: the block writes its 256 pixels x 128 B fully coalesced.
-  __shared__ uint4 tile[256 * 8];
-  const long long npix = (long long)T * H * W;
-  const long long plane = (long long)H * W;
-  for (long long base = (long long)blockIdx.x * 256; base < npix; base += (long long)gridDim.x * 256) {
-    const long long i = base + threadIdx.x;
-    if (i < npix) {
-      const int x = (int)(i % W);
-      const int y = (int)((i / W) % H);
-      const int t = (int)(i / plane);
-      float v[40];
-#pragma unroll
-      for (int k = 36; k < 40; ++k) v[k] = 0.f;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        const bool ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float f = 0.f;
-          if (ok) {
-            if (c < in_c) f = __ldg(in + ((long long)t * in_c + c) * plane + (long long)yy * W + xx);
-            else if (nmap) f = __ldg(nmap + (long long)t * plane + (long long)yy * W + xx);
-          }
-          v[tap * 4 + c] = f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (j < 5) {
-          u.x = pack2<BF16>(v[8 * j + 0], v[8 * j + 1]); u.y = pack2<BF16>(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack2<BF16>(v[8 * j + 4], v[8 * j + 5]); u.w = pack2<BF16>(v[8 * j + 6], v[8 * j + 7]);
-        }
-        tile[threadIdx.x * 8 + (j ^ (threadIdx.x & 7))] = u;
-      }
-    }
-    __syncthreads();
-    uint4* o = reinterpret_cast<uint4*>(out) + base * 8;
-    const long long lim = (npix - base < 256 ? npix - base : 256) * 8;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = r * 256 + threadIdx.x;        // chunk index inside the block's 32 KB
-      const int px = e >> 3, j = e & 7;
-      if (e < lim) o[e] = tile[px * 8 + (j ^ (px & 7))];
-    }
-    __syncthreads();
-  }
 }
 
 }  // namespace bsvd
@@ -727,7 +715,13 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
   return 0;
 }
 
-static int check_hw(int T, int in_c, int H, int W, bool has_nmap) {
+static int check_hw(int T, int in_c, int H, int W, bool has_nmap, int net_in_ch = 4) {
+  if (net_in_ch == 3) {
+    if (in_c != 3 || has_nmap)
+      return fail("blind model: input must have 3 channels and no noise map (got in_c=%d, noise_map=%d)",
+                  in_c, (int)has_nmap);
+    has_nmap = true;   // fall through the shape checks below
+  }
   if (T < 1) return fail("T must be >= 1");
   if (H < 4 || W < 4 || (H % 4) || (W % 4))
     return fail("H and W must be multiples of 4 (got %dx%d); the reference fails at the skip add "
@@ -746,11 +740,11 @@ const char* bsvd_version(void) { return "bsvd_b200 0.1 (sm_100a, tcgen05/TMEM/TM
 int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
   if (!cfg || !out) return fail("null argument");
   if (!(cfg->chns[0] == 64 && cfg->chns[1] == 128 && cfg->chns[2] == 256 && cfg->mid_ch == 64 &&
-        cfg->interm_ch == 64 && cfg->in_ch == 4 && cfg->out_ch == 3 && cfg->act_relu6 == 1 &&
-        cfg->norm_none == 1))
+        cfg->interm_ch == 64 && (cfg->in_ch == 4 || cfg->in_ch == 3) && cfg->out_ch == 3 &&
+        cfg->act_relu6 == 1 && cfg->norm_none == 1))
     return fail("only the BSVD-64 configuration of options/test/bsvd_c64.yml is implemented on the "
-                "GPU path (chns=[64,128,256], mid_ch=64, interm_ch=64, in_ch=4, out_ch=3, "
-                "norm='none', act='relu6'); there is no CPU fallback");
+                "GPU path (chns=[64,128,256], mid_ch=64, interm_ch=64, in_ch=4 (or 3 = blind), "
+                "out_ch=3, norm='none', act='relu6'); there is no CPU fallback");
   if (cfg->precision != BSVD_PREC_FP16 && cfg->precision != BSVD_PREC_BF16)
     return fail("unknown precision %d", cfg->precision);
   int ndev = 0;
@@ -854,7 +848,7 @@ size_t bsvd_workspace_bytes(const bsvd_handle* h) { return h ? h->ws_bytes : 0; 
 int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
                       int in_c, int H, int W, void* stream) {
   if (!h || !in || !out) return fail("null argument");
-  if (check_hw(T, in_c, H, W, noise_map != nullptr)) return 1;
+  if (check_hw(T, in_c, H, W, noise_map != nullptr, h->cfg.in_ch)) return 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
   if (build_clip_plan(h, in, noise_map, out, T, in_c, H, W)) return 1;
@@ -869,13 +863,10 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
     evs = &h->ev_sets[h->ev_used++];
     CUDA_TRY(cudaEventRecord((*evs)[0], st));
   }
-  const long long npix = (long long)T * H * W;
-  const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 8);
-  if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
-  else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(in, noise_map, h->bufP, T, in_c, H, W);
-  CUDA_TRY(cudaGetLastError());
+  // stage 0 (input staging) is fused into temp1.inc.convblock.0 (first_conv.cuh)
+  h->plan[0].first_in = in; h->plan[0].first_nmap = noise_map; h->plan[0].first_inc = in_c;
   if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
-  int launches = 1;
+  int launches = 0;
   h->plan[15].p.resid_in = in;          // temp1 residual reads the raw input (skip1)
   h->plan[15].p.resid_C = in_c;
   h->plan[BSVD_NUM_LAYERS - 1].p.out = out;
@@ -900,7 +891,7 @@ static int ensure_dev(float** p, size_t* cur, size_t need) {
 int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nmap_host,
                            float* out_host, int T, int in_c, int H, int W, void* stream) {
   if (!h || !in_host || !out_host) return fail("null argument");
-  if (check_hw(T, in_c, H, W, nmap_host != nullptr)) return 1;
+  if (check_hw(T, in_c, H, W, nmap_host != nullptr, h->cfg.in_ch)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t plane = (size_t)H * W * sizeof(float);
   if (ensure_dev(&h->d_in, &h->d_in_bytes, plane * T * in_c)) return 1;
@@ -923,7 +914,7 @@ int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nm
 int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const float* nmap_host,
                                  float* out_host, int T, int in_c, int H, int W, void* stream) {
   if (!h || !in_host || !out_host) return fail("null argument");
-  if (check_hw(T, in_c, H, W, nmap_host != nullptr)) return 1;
+  if (check_hw(T, in_c, H, W, nmap_host != nullptr, h->cfg.in_ch)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!h->s_h2d) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -1038,7 +1029,7 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
                      int in_c, int H, int W, int* produced, void* stream) {
   if (produced) *produced = 0;
   if (!h || !out) return fail("null argument");
-  if (check_hw(1, frame ? in_c : 4, H, W, frame ? noise_map != nullptr : false)) return 1;
+  if (check_hw(1, frame ? in_c : h->cfg.in_ch, H, W, frame ? noise_map != nullptr : false, h->cfg.in_ch)) return 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
   auto& S = h->stream;
@@ -1059,13 +1050,6 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
     if (noise_map)
       CUDA_TRY(cudaMemcpyAsync(slot + 3 * plane, noise_map, plane * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
-    const long long npix = (long long)plane;
-    const int pgrid = (int)std::min<long long>((npix + 255) / 256, (long long)num_sms() * 8);
-    uint16_t* P = reinterpret_cast<uint16_t*>(S.ring[0][kRingP]);
-    if (h->bf16) prep_patches_kernel<true><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);
-    else prep_patches_kernel<false><<<pgrid, 256, 0, st>>>(slot, nullptr, P, 1, 4, H, W);
-    CUDA_TRY(cudaGetLastError());
-    ++launches;
     ++S.n_in;
   } else {
     S.ended = true;
@@ -1091,6 +1075,10 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
       if (l == 10) p.skip = S.ring[b][kRingX1] + (size_t)(f % kRingSlots[kRingX1]) * ring_slot_bytes(kRingX1, H, W);
       if (l == 13) p.skip = S.ring[b][kRingX0] + (size_t)(f % kRingSlots[kRingX0]) * ring_slot_bytes(kRingX0, H, W);
       const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+      if (l == 0 && b == 0) {
+        L.first_in = S.raw + (size_t)(f % 9) * 4 * plane;   // raw ring slot holds all 4 channels
+        L.first_nmap = nullptr; L.first_inc = h->cfg.in_ch;   // blind model: planes 0..2 only
+      }
       if (l == 15 && b == 0) {
         p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
         p.aux_out = S.aux + (size_t)(f % 9) * aux_slot;

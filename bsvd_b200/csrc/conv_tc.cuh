@@ -110,6 +110,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   // relaxed (see mbar_arrive_cluster): no memory fence wanted on the accumulator hand-back
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_release(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

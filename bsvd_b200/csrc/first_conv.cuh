@@ -1,0 +1,207 @@
+// first_conv.cuh — temp1.inc.convblock.0 (4 -> 64 channels, ReLU6) fused with the input staging.
+//
+// Reference: the torch.cat([input, noise_map]) of BSVD.forward (bsvd_arch.py:492-493) and the first
+// nn.Conv2d of InputCvBlock (bsvd_arch.py:207-209).  With only 4 input channels the 3x3x4 patch of a
+// pixel (36 values) fits one 128-byte K row, so the conv is a single-tap GEMM with K = 64 (36 used).
+// Instead of materialising the patches in HBM (a 663 MB round trip per 10-frame clip) four producer
+// warps build them directly in shared memory, in the SWIZZLE_128B K-major layout tcgen05.mma reads:
+//   warps 0-7  patch producers, two groups of 4 warps taking alternate tiles: fp32 NCHW (+ noise
+//              map) -> 16-bit swizzled rows, fence.proxy.async
+//   warp  8    MMA issuer (8 MMAs per 2-row tile, filter bank resident)
+//   warps 9-16 epilogue (shared with conv_tc.cuh: bias, ReLU6, staged coalesced NHWC stores)
+#pragma once
+#include "conv_tc.cuh"
+
+namespace bsvd {
+
+constexpr int kFirstR = 2;
+constexpr int kFirstThreads = 32 * 17;
+constexpr int kFirstProducers = 128;
+constexpr int kFirstStages = 4;
+constexpr uint32_t kFirstAStage = kFirstR * kRunPx * 128;   // 32 KB
+constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
+constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * kStageBytesPerWarp;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kFirstThreads, 1)
+first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, int in_c,
+                  const __grid_constant__ ConvParams p) {
+  constexpr int NT = 64;
+  constexpr int kAccCols = kFirstR * NT;
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kFirstStages + 5];
+  __shared__ __align__(16) float bias_s[NT];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = a_base + kFirstStages * kFirstAStage;
+  const uint32_t stg_base = w_base + kFirstW;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kFirstStages + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * kFirstStages + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kFirstStages + 2 + b); };
+  const uint32_t w_full = bar0 + 8u * (2 * kFirstStages + 4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFirstStages; ++s) {
+      mbar_init(a_full(s), kFirstProducers);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 8);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < NT) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  // K slots 36..63 of every patch row are zero for the whole kernel: clear the stages once
+  for (uint32_t off = threadIdx.x * 16; off < kFirstStages * kFirstAStage; off += kFirstThreads * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + off), "r"(0) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp < 8) {
+    // =================================== patch producers ===================================
+    // thread = one x position of the 128-px run; it builds the patch rows of both tile rows
+    // (they share two of their three input rows).  Group g = warp/4 handles every second tile, so
+    // the global-load latency of one group's tile overlaps the stores of the other's.
+    const int i = threadIdx.x & 127;             // 0..127
+    const int grp = threadIdx.x >> 7;            // 0 / 1
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    uint32_t it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const uint32_t sa = it % kFirstStages, pa = (it / kFirstStages) & 1;
+      const TileCoord tc = decode_tile<kFirstR>(p, tile);
+      const int x = tc.x0 + i;
+      // 4 input rows (y0-1 .. y0+2) x 3 columns x 4 channels
+      float v[4][3][4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int yy = tc.y0 - 1 + rr;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = x - 1 + dx;
+          const bool ok = (yy >= 0) && (yy < p.H) && (xx >= 0) && (xx < p.W);
+          const long long o = static_cast<long long>(yy) * p.W + xx;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float f = 0.f;
+            if (ok) {
+              if (c < in_c) f = __ldg(in + (static_cast<long long>(tc.t) * in_c + c) * plane + o);
+              else if (nmap) f = __ldg(nmap + static_cast<long long>(tc.t) * plane + o);
+            }
+            v[rr][dx][c] = f;
+          }
+        }
+      }
+      mbar_wait(a_empty(sa), pa ^ 1);
+      const uint32_t stage = a_base + sa * kFirstAStage;
+#pragma unroll
+      for (int r = 0; r < kFirstR; ++r) {
+        // k = tap*4 + c, tap = dy*3 + dx  ->  chunk j holds taps 2j, 2j+1 (chunk 4: tap 8 + zeros)
+        const uint32_t row = stage + r * (kRunPx * 128) + i * 128;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          float f[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int tap = 2 * j + h;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[4 * h + c] = (tap < 9) ? v[r + tap / 3][tap % 3][c] : 0.f;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(row + ((j ^ (i & 7)) << 4)), "r"(pack2<BF16>(f[0], f[1])),
+                         "r"(pack2<BF16>(f[2], f[3])), "r"(pack2<BF16>(f[4], f[5])),
+                         "r"(pack2<BF16>(f[6], f[7]))
+                       : "memory");
+        }
+      }
+      fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
+      mbar_arrive_release(a_full(sa));
+    }
+  } else if (warp == 8) {
+    // ====================================== MMA issuer ======================================
+    const uint32_t idesc = make_idesc(NT, BF16 ? 1 : 0);
+    const uint32_t leader = elect_one();
+    constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);
+    const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+    if (leader) {
+      mbar_expect_tx(w_full, kFirstW);
+      bulk_load(w_base, p.wpack, kFirstW, w_full);
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    uint32_t sa = 0, pa = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(acc_empty(buf), acc_phase ^ 1);
+      mbar_wait(a_full(sa), pa);
+      tc_fence_after();
+      const uint32_t a_lo0 = (((a_base + sa * kFirstAStage) & 0x3FFFFu) >> 4) | (1u << 16);
+      if (leader) {
+#pragma unroll
+        for (int r = 0; r < kFirstR; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + buf * kAccCols + r * NT,
+                     desc_hi | (a_lo0 + static_cast<uint32_t>(r * (kRunPx * 8)) + k * 2u),
+                     desc_hi | (b_lo0 + k * 2u), idesc, k > 0 ? 1u : 0u);
+        umma_commit(a_empty(sa));
+        umma_commit(acc_full(buf));
+      }
+      __syncwarp();
+      if (++sa == kFirstStages) { sa = 0; pa ^= 1; }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int ew = warp - 9;                   // 0..7
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    constexpr int G = NT / 32;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile<kFirstR>(p, tile);
+      const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(acc_full(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
+      const int u0 = half * 2;                 // 4 units (2 rows x 2 column groups), 2 per warp half
+      uint32_t va[32], vb[32];
+      const uint4 nosk[4] = {};
+      tmem_ld32(tacc + (u0 / G) * NT + (u0 % G) * 32, va);
+      tmem_ld32(tacc + ((u0 + 1) / G) * NT + ((u0 + 1) % G) * 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      epilogue_unit<BF16, EPI_RELU6>(p, tc, tc.y0 + u0 / G, (u0 % G) * 32, va, nosk, bias_s, stg, quad, lane);
+      epilogue_unit<BF16, EPI_RELU6>(p, tc, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bias_s, stg, quad, lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace bsvd

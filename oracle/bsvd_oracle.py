@@ -62,10 +62,11 @@ _BSVD_LAYER_KEYS = (
 SHIFT_LAYERS = (3, 4, 6, 7, 8, 9, 11, 12)
 
 
-def layer_shapes(block: int):
-    """[(cout, cin, stride)] of the 16 convs of DenBlock `block` (0 = temp1, 1 = temp2)."""
+def layer_shapes(block: int, in_ch: int = IN_CH):
+    """[(cout, cin, stride)] of the 16 convs of DenBlock `block` (0 = temp1, 1 = temp2).
+    in_ch=3 is the blind variant (InputCvBlock(blind=True), bsvd_arch.py:204-205)."""
     c0, c1, c2 = CHNS
-    cin = IN_CH if block == 0 else MID_CH
+    cin = in_ch if block == 0 else MID_CH
     cout = MID_CH if block == 0 else OUT_CH
     return [
         (INTERM_CH, cin, 1), (c0, INTERM_CH, 1),
@@ -94,7 +95,8 @@ def bsvd_keys():
     return keys
 
 
-def make_synthetic_params(seed: int = 0, weight_scale: float = 0.5, prefix: str = "base_model."):
+def make_synthetic_params(seed: int = 0, weight_scale: float = 0.5, prefix: str = "base_model.",
+                          in_ch: int = IN_CH):
     """Seeded synthetic checkpoint in the TSN key layout (SURVEY §8d recipe).
 
     kaiming_normal_(nonlinearity='relu') statistics (wnet_models.py:155-162: std = sqrt(2/fan_in))
@@ -105,7 +107,7 @@ def make_synthetic_params(seed: int = 0, weight_scale: float = 0.5, prefix: str 
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
     for blk in range(2):
-        for name, (co, ci, _s) in zip(_TSN_LAYER_KEYS, layer_shapes(blk)):
+        for name, (co, ci, _s) in zip(_TSN_LAYER_KEYS, layer_shapes(blk, in_ch)):
             fan_in = ci * 9
             w = rng.standard_normal((co, ci, 3, 3), dtype=np.float32) * np.float32(
                 weight_scale * np.sqrt(2.0 / fan_in))

@@ -44,7 +44,7 @@ def test_matches_reference_fixture(path, prec):
         assert err <= TOL[prec], err
     else:
         assert err <= (4e-3 if prec == "fp16" else 4e-2) * float(ref.abs().max()), err
-    assert net.last_launch_count == 33
+    assert net.last_launch_count == 32      # 32 fused stages, no separate staging kernel
 
 
 @pytest.mark.parametrize("shape", [(5, 64, 96), (2, 136, 264), (3, 36, 260), (12, 16, 16)])
@@ -286,3 +286,27 @@ def test_denoise_sequence_pad_clamp_crop_like_the_reference_callers():
     assert got.shape == (3, 3, 30, 45)
     assert float((got - ref).abs().max()) <= TOL["fp16"]
     assert float(got.min()) >= 0.0 and float(got.max()) <= 1.0
+
+
+def test_blind_variant_three_channel_input():
+    """blind=True (README.md:66-72 blind checkpoint; InputCvBlock drops the noise map,
+    bsvd_arch.py:204-205): 3-channel frames, no noise map; clip and stream schedules vs the oracle."""
+    from bsvd_b200.arch import BSVD
+    sd = O.make_synthetic_params(0, 0.5, in_ch=3)
+    net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+               act='relu6', blind=True, pretrain_ckpt=None)
+    net.load_tsn_state(sd)
+    net = net.cuda().eval()
+    x, _ = O.make_synthetic_clip(4, 36, 52, seed=60)
+    x3 = x[:, :3].contiguous()
+    ref = O.forward_clip(O.layers_from_tsn_state(sd), x3)
+    with torch.no_grad():
+        y = net(x3[None].cuda())[0]
+        net.reset()
+        outs, _ = _drive_stream(net, x3)
+        net.reset()
+    assert float((y.float().cpu() - ref).abs().max()) <= TOL["fp16"]
+    assert torch.equal(torch.cat([o for o in outs if o is not None]), y)
+    from bsvd_b200.capi import BsvdError
+    with pytest.raises(BsvdError):
+        net(x[None].cuda())        # a 4-channel frame is not what a blind model takes

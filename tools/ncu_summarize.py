@@ -25,7 +25,7 @@ for i, r in enumerate(data):
     name = r[col["Kernel Name"]]
     m = re.search(r"conv3x3_tc_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d+)>", name)
     short = f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}> cta2={m.group(4)} mask={m.group(5)}" if m else name.split("(")[0][-40:]
-    key = f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}>" if m else short
+    key = f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}>" if m else ("first_conv_kernel" if "first_conv" in name else "final_conv_kernel" if "final_conv" in name else short)
     t = to_us(g(r, "gpu__time_duration.sum"), unit("gpu__time_duration.sum"))
     rd = to_bytes(g(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum"))
     wr = to_bytes(g(r, "dram__bytes_write.sum"), unit("dram__bytes_write.sum"))
