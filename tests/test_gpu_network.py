@@ -310,3 +310,21 @@ def test_blind_variant_three_channel_input():
     from bsvd_b200.capi import BsvdError
     with pytest.raises(BsvdError):
         net(x[None].cuda())        # a 4-channel frame is not what a blind model takes
+
+
+def test_long_clip_crosses_2G_element_offsets():
+    """70 frames at 540x960: every full-resolution tensor holds 2.3e9 elements (> 2^31), so frame
+    offsets must be 64-bit everywhere.  Property (no oracle at this size): an output frame depends on
+    inputs at most 16 frames away, so the tail of the long clip equals the tail of its last 30
+    frames run alone, bit for bit."""
+    net, _ = make_net()
+    short, _ = O.make_synthetic_clip(30, 540, 960, seed=70)
+    head = short[:20].flip(0).repeat(2, 1, 1, 1)            # 40 more frames of plausible content
+    x = torch.cat([head, short], dim=0).cuda()              # [70,4,540,960]
+    with torch.no_grad():
+        long_out = net(x[None])[0]
+        tail = long_out[62:].clone()
+        del long_out
+        short_out = net(x[None, 40:])[0]
+    assert torch.equal(tail, short_out[22:])
+    assert bool(torch.isfinite(tail).all())
