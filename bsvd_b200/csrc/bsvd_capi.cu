@@ -148,6 +148,7 @@ struct StageSpec {
   int stride = 1;
   bool relu6 = false, pixshuf = false, skip = false, shift = false;
   bool resid_in = false, final_out = false, first_im2col = false;
+  bool stacked = false;   // 64->64 stride-1 stage with the vertical taps stacked in N (conv_tc.cuh mode 2)
   // derived
   int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
   void derive() {
@@ -159,11 +160,17 @@ struct StageSpec {
     cin_chunks = first_im2col ? 1 : cin / kChunk;
     tap_begin = first_im2col ? 4 : 0;
     tap_end = first_im2col ? 5 : 9;
+    static const int stack_on = [] { const char* e = getenv("BSVD_B200_STACK"); return e ? atoi(e) : 1; }();
+    static const int cta2_on = [] { const char* e = getenv("BSVD_B200_NO_CTA2"); return (e && e[0] == '1') ? 0 : 1; }();
+    stacked = stack_on && cta2_on && cin == 64 && cout == 64 && stride == 1 && !first_im2col &&
+              !final_out && !pixshuf && !skip;
+    if (stacked) { tap_begin = 0; tap_end = 3; }   // three dx slabs of [192 rows per CTA][64]
   }
   int ntaps() const { return tap_end - tap_begin; }
   int n_tiles() const { return gemm_n / ntile; }
   size_t pack_elems() const {
     if (final_out) return (size_t)3 * kFinalN * kChunk;   // [dx][dy*3+co][64]
+    if (stacked) return (size_t)3 * 2 * 192 * kChunk;     // [dx][cta rank][192 rows][64]
     return (size_t)n_tiles() * cin_chunks * ntaps() * ntile * kChunk;
   }
 };
@@ -198,6 +205,29 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
             pack[((size_t)dx * kFinalN + n) * kChunk + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = to16(v, bf16);
           }
         }
+    return;
+  }
+  if (s.stacked) {
+    // conv_tc.cuh mode 2.  Per dx, per CTA of the pair, four slabs (row ranges inside the CTA's 24 KB):
+    //   [0,32)    hr 0: dy0, couts [32*rank, +32)          -> acc0
+    //   [32,96)   hr 1: rank 0 = dy1 (acc0), rank 1 = dy0 (acc1)
+    //   [96,160)  hr 2: rank 0 = dy2 (acc0), rank 1 = dy1 (acc1)
+    //   [160,192) hr 3: dy2, couts [32*rank, +32)          -> acc1
+    for (int dx = 0; dx < 3; ++dx)
+      for (int rank = 0; rank < 2; ++rank) {
+        uint16_t* cta = pack.data() + ((size_t)dx * 2 + rank) * 192 * kChunk;
+        for (int row = 0; row < 192; ++row) {
+          int dy, co, local;   // local = row index inside its slab (swizzle phase)
+          if (row < 32) { dy = 0; co = rank * 32 + row; local = row; }
+          else if (row < 96) { dy = rank == 0 ? 1 : 0; co = row - 32; local = row - 32; }
+          else if (row < 160) { dy = rank == 0 ? 2 : 1; co = row - 96; local = row - 96; }
+          else { dy = 2; co = rank * 32 + (row - 160); local = row - 160; }
+          for (int k = 0; k < kChunk; ++k) {
+            const float v = w[((size_t)co * s.cin + k) * 9 + dy * 3 + dx];
+            cta[(size_t)row * kChunk + (((k >> 3) ^ (local & 7)) << 3) + (k & 7)] = to16(v, bf16);
+          }
+        }
+      }
     return;
   }
   const int nt_count = s.n_tiles();
@@ -408,8 +438,13 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.mode = (s.stride == 2) ? 1 : 0;
   p.cin_total = s.cin;
   p.w_stage_bytes = (uint32_t)s.ntile * 128u / (cta2 ? 2u : 1u);
+  p.w_rows_cta = s.ntile / 2;
+  const bool stacked = s.stacked;
+  if (stacked && !cta2) return fail("stacked filter layout needs the CTA-pair kernel");
+  if (stacked) { p.w_stage_bytes = 192u * 128u; p.w_rows_cta = 192; }
   const size_t budget = kSmemOptIn - 1024 - kStagingBytes;   // minus alignment slack and staging
-  if (p.mode == 0) {
+  if (stacked) p.mode = 2;
+  if (p.mode != 1) {
     p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
     p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
     p.a_stages = 2;
@@ -455,11 +490,11 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
 
   const int cin_map = s.first_im2col ? kChunk : s.cin;
-  int rc = (p.mode == 0) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
+  int rc = (p.mode != 1) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
                          : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
   if (rc) return rc;
   if (cta2) {
-    rc = make_map_w(&L->map_w, sd.wpack, s.pack_elems() / kChunk, s.ntile / 2);
+    rc = make_map_w(&L->map_w, sd.wpack, s.pack_elems() / kChunk, p.w_rows_cta);
     if (rc) return rc;
   } else {
     L->map_w = L->map;   // unused
@@ -1123,6 +1158,9 @@ int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, con
   s.shift = d->flags & BSVD_EPI_SHIFT_STORE;
   if (s.pixshuf && s.stride == 2) return fail("pixel shuffle and stride 2 cannot be combined");
   s.derive();
+  if (d->debug_variant & (32 | (1 << 20))) {   // debug: single-CTA kernels / plain (unstacked) 64->64
+    s.stacked = false; s.tap_begin = 0; s.tap_end = 9;
+  }
   const int bf16 = d->precision == BSVD_PREC_BF16;
   if (upload_stage(sd, w, bias, bf16)) return 1;
   StageIO io;

@@ -29,6 +29,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace bsvd {
 
 constexpr int kRunPx = 128;        // pixels per MMA row-run (UMMA M)
@@ -62,7 +64,9 @@ struct ConvParams {
   int xblocks, yblocks; // ceil(W/128), ceil(H/R)
   int total_tiles;      // 1-CTA: positions*n_tiles; CTA pair: ceil(positions/2)*n_tiles
   int positions;        // T*yblocks*xblocks pixel tiles
-  int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2)
+  int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2),
+                        // 2 = halo with the vertical taps stacked in N (64->64 stages, see below)
+  int w_rows_cta;       // CTA pair: filter rows one CTA stages per W stage
   int cin_total;        // Cin (stride-2 coordinate math)
   // ---- pipeline ----
   int a_stages, w_stages;
@@ -285,6 +289,16 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(0) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -382,8 +396,24 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // Skip-tensor operand of one unit (lane = pixel): 64 contiguous bytes at the (PixelShuffle-
 // scattered) output location.  Issued one unit ahead of its use so the L2 round trip overlaps the
 // arithmetic of the previous unit.
-template <int MASK>
-__device__ __forceinline__ void skip_prefetch(const ConvParams& p, const TileCoord& tc, int y,
+// Register-resident copy of the fields the epilogue touches per unit (ConvParams lives in the
+// kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
+// critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
+struct EpiParams {
+  int flags, T, H, W, out_C, out_W, fold, ring_mode, skip_C, resid_C, desc_variant;
+  void* out; void* out_prev; void* out_next; void* aux_out;
+  const void* skip; const float* resid_in;
+  long long out_frame_stride, skip_frame_stride;
+  __device__ __forceinline__ explicit EpiParams(const ConvParams& p)
+      : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W), fold(p.fold),
+        ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
+        out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
+        resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
+        skip_frame_stride(p.skip_frame_stride) {}
+};
+
+template <int MASK, class P>
+__device__ __forceinline__ void skip_prefetch(const P& p, const TileCoord& tc, int y,
                                               int nbase, int quad, int lane, uint4 (&sk)[4]) {
   // Coalesced layout (same as the store phase): lane = (pixel group lane>>2, 16-byte chunk lane&3),
   // so four lanes fetch the 64 contiguous bytes of one pixel: full sectors, 8 lines per request.
@@ -411,8 +441,8 @@ __device__ __forceinline__ void skip_prefetch(const ConvParams& p, const TileCoo
 }
 
 // MASK = set of EPI_* features compiled into this instance (runtime flags are a subset of it).
-template <bool BF16, int MASK>
-__device__ __forceinline__ void epilogue_unit(const ConvParams& p, const TileCoord& tc, int y,
+template <bool BF16, int MASK, class P>
+__device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, int y,
                                               int nbase, const uint32_t (&v)[32],
                                               const uint4 (&sk)[4],
                                               const float* bias_s, uint32_t stg, int quad,
@@ -637,6 +667,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if constexpr (NTILE == 64 && R == 2 && CTA2) {
+    if (p.mode == 2) {
+      // stacked mode accumulates from the first MMA on: start from zeroed accumulators
+      if (warp >= 2) {
+        const uint32_t lb = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int part = (warp - 2) >> 2;
+        for (int c = part * 32; c < kTmemCols; c += 32 * (EW / 4)) tmem_st32_zero(tmem_base + lb + c);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      cluster_sync_all();
+      tc_fence_after();
+    }
+  }
   pdl_launch_dependents();
   pdl_wait();            // everything above touched only weights/bias; activations come next
 
@@ -653,7 +697,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
         for (int c = 0; c < p.cin_chunks; ++c) {
-          if (p.mode == 0) {
+          if (p.mode != 1) {
             mbar_wait(a_empty(sa), pa ^ 1);
             if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
             if constexpr (CTA2)
@@ -687,7 +731,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if constexpr (CTA2) {
                 // each CTA of the pair stages half of the N rows of this (chunk, tap) filter slab
                 tma_load_2d_2sm(w_base + sw * p.w_stage_bytes, &map_w, w_full(sw), 0,
-                                static_cast<int>(blk) * NTILE + static_cast<int>(rank) * (NTILE / 2));
+                                (static_cast<int>(blk) * 2 + static_cast<int>(rank)) * p.w_rows_cta);
               } else {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + blk * p.w_stage_bytes;
                 bulk_load(w_base + sw * p.w_stage_bytes, src, p.w_stage_bytes, w_full(sw));
@@ -714,6 +758,55 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool no_load = (p.desc_variant & 16) != 0;
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       uint32_t it = 0;
+      bool stacked = false;
+      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = (p.mode == 2);
+      if (stacked) {
+        // ---- 64->64 stages, vertical taps stacked in N -------------------------------------------
+        // The two output-row accumulators sit side by side in TMEM (columns [0,64) and [64,128)).
+        // Haloed INPUT row hr feeds output row hr-dy with filter row dy, so one MMA per (dx, k-step)
+        // with the filter blocks ordered to match covers all output rows it touches:
+        //   hr 0: [dy0]      -> acc0          N=64      hr 2: [dy2|dy1] -> acc0|acc1   N=128
+        //   hr 1: [dy1|dy0]  -> acc0|acc1     N=128     hr 3: [dy2]     -> acc1        N=64
+        // 48 MMAs per tile instead of 72 and a quarter fewer operand bytes, same FLOPs.  Every MMA
+        // accumulates; the epilogue hands the accumulators back zeroed.
+        const uint32_t idesc64 = make_idesc(64, BF16 ? 1 : 0, 256);
+        const uint32_t idesc128 = make_idesc(128, BF16 ? 1 : 0, 256);
+        const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
+          const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+          mbar_wait(acc_empty(buf), acc_phase ^ 1);
+          if (!no_load) {
+            mbar_wait(a_full(sa), pa);
+            if (it == 0) { mbar_wait(w_full(0), 0); mbar_wait(w_full(1), 0); mbar_wait(w_full(2), 0); }
+          }
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+          const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (leader && !skip_mma) {
+#pragma unroll
+            for (int hr = 0; hr < 4; ++hr) {
+              const uint32_t col0 = (hr == 3) ? 64u : 0u;
+              const uint32_t boff = (hr == 0 ? 0u : hr == 1 ? 4096u : hr == 2 ? 12288u : 20480u) >> 4;
+              const uint32_t idesc_h = (hr == 0 || hr == 3) ? idesc64 : idesc128;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = desc_hi | (a_lo0 + static_cast<uint32_t>((hr * kHaloPx + dx) * 8) + k * 2u);
+                  const uint64_t bd = desc_hi | (b_lo0 + static_cast<uint32_t>(dx * (24576 >> 4)) + boff + k * 2u);
+                  umma_f16_2sm(tmem_acc + col0, ad, bd, idesc_h, 1u);
+                }
+              }
+            }
+          }
+          if (leader) {
+            umma_commit_2sm(a_empty(sa));
+            umma_commit_2sm(acc_full(buf));
+          }
+          __syncwarp();
+          if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+        }
+      } else
       for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
         const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
       const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -785,6 +878,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int half = ew >> 2;                  // EW/4 warps share a TMEM lane quadrant and split the units
     const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    // register copy of the epilogue parameters, except in the register-starved general instance
+    using EP = typename std::conditional<(MASK & EPI_SKIP) != 0, const ConvParams&, const EpiParams>::type;
+    EP e(p);
     uint32_t it = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
@@ -800,20 +896,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // skip operand of the first unit: issued before waiting for the accumulator, so its latency
       // is covered by the MMAs of this very tile; later units are prefetched one unit ahead
       uint4 ska[4] = {}, skb[4] = {};
-      skip_prefetch<MASK>(p, tc, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
+      skip_prefetch<MASK>(e, tc, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
       // accumulator drained: the (leader's) MMA warp may reuse the buffer
+      bool stacked = false;
+      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = (p.mode == 2);
       auto release_acc = [&]() {
+        if (stacked) tmem_st_wait();           // the zeros written behind the loads have landed
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if constexpr (CTA2) mbar_arrive_cluster(acc_empty(buf), 0); else mbar_arrive(acc_empty(buf));
         }
       };
-      const bool live = tc.t < p.T;            // false only for the padding tile of an odd pair
-      const bool work = live && !(p.desc_variant & 4);
+      const bool live = tc.t < e.T;            // false only for the padding tile of an odd pair
+      const bool work = live && !(e.desc_variant & 4);
       uint32_t va[32], vb[32];
       tmem_ld32(tacc + (u0 / G) * NTILE + (u0 % G) * 32, va);
       // two units per iteration (register double buffering); NOT unrolled further: the epilogue
@@ -821,29 +920,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll 1
       for (int k = 0; k < kMine; k += 2) {
         tmem_ld_wait();
+        if (stacked) { const int u = u0 + k; tmem_st32_zero(tacc + (u / G) * NTILE + (u % G) * 32); }
         if (k + 1 < kMine) {
           const int u = u0 + k + 1;
           tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
-          skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
+          skip_prefetch<MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
         } else {
           release_acc();
         }
         if (work) {
           const int u = u0 + k;
-          epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
+          epilogue_unit<BF16, MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
         }
         if (k + 1 < kMine) {
           tmem_ld_wait();
+          if (stacked) { const int u = u0 + k + 1; tmem_st32_zero(tacc + (u / G) * NTILE + (u % G) * 32); }
           if (k + 2 < kMine) {
             const int u = u0 + k + 2;
             tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
-            skip_prefetch<MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
+            skip_prefetch<MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
           } else {
             release_acc();
           }
           if (work) {
             const int u = u0 + k + 1;
-            epilogue_unit<BF16, MASK>(p, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
+            epilogue_unit<BF16, MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
           }
         }
       }
