@@ -962,9 +962,11 @@ int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const flo
   }
   const int k = (int)(h->host_calls & 1);
   const size_t plane = (size_t)H * W * sizeof(float);
-  if (ensure_dev(&h->pin[k], &h->pin_bytes[k], plane * T * in_c)) return 1;
-  if (ensure_dev(&h->pout[k], &h->pout_bytes[k], plane * T * 3)) return 1;
-  if (nmap_host && ensure_dev(&h->pnm[k], &h->pnm_bytes[k], plane * T)) return 1;
+  for (int b = 0; b < 2; ++b) {   // both staging sets up front: cudaMalloc synchronises the device
+    if (ensure_dev(&h->pin[b], &h->pin_bytes[b], plane * T * in_c)) return 1;
+    if (ensure_dev(&h->pout[b], &h->pout_bytes[b], plane * T * 3)) return 1;
+    if (nmap_host && ensure_dev(&h->pnm[b], &h->pnm_bytes[b], plane * T)) return 1;
+  }
   if (h->host_calls >= 2) {
     CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[k], 0));   // forward i-2 has consumed pin[k]
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_d2h[k], 0));          // copy-out i-2 has drained pout[k]
