@@ -356,6 +356,7 @@ def run_b200(args):
         "whole_net": whole,
         "kernels": per_kernel,
         "conv_ms_per_step": conv_ms,
+        "stage_ms": [round(stage_ms[s] / max(passes.value, 1), 4) for s in range(1, capi.NUM_STAGES)],
         "parity": parity,
         "cpu_baseline": cpu,
         "workspace_bytes": int(lib.bsvd_workspace_bytes(net._handle)),
