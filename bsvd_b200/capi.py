@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbsvd_b200.so")
+# BSVD_B200_LIB: development override (A/B timing of two builds on the same box)
+LIB_PATH = os.environ.get("BSVD_B200_LIB") or os.path.join(_HERE, "lib", "libbsvd_b200.so")
 
 NUM_LAYERS = 32
 PREC_FP16, PREC_BF16 = 0, 1

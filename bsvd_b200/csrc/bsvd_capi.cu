@@ -261,6 +261,7 @@ struct StageDev {
   StageSpec spec;
   void* wpack = nullptr;
   float* bias = nullptr;
+  std::vector<float> bias_h;   // host copy: travels in the kernel parameter bank (ConvParams::bias_c)
   bool loaded = false;
 };
 
@@ -338,6 +339,8 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
 constexpr int kMaskPlain = EPI_RELU6;
 constexpr int kMaskShift = EPI_RELU6 | EPI_SHIFT;
 constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
+constexpr int kMaskUp = EPI_PIXSHUF | EPI_SKIP;                  // upc1.convblock.0
+constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0
 constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
@@ -347,6 +350,10 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
     if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
     if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
+    if constexpr (NTILE == 256) {
+      if ((f & ~kMaskUp) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUp, 8>(L, st);
+      if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpShift, 8>(L, st);
+    }
   }
   return launch_inst<NTILE, R, BF16, true, kMaskAll, 8>(L, st);
 }
@@ -382,6 +389,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   const StageSpec& s = sd.spec;
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
+  if (sd.bias_h.size() > (size_t)kMaxBias) return fail("bias does not fit the parameter bank");
+  std::copy(sd.bias_h.begin(), sd.bias_h.end(), p.bias_c);
   // CTA pairs (cta_group::2): one M=256 MMA drives two pixel tiles and each CTA stages only half
   // of the filter slab.  The 3-channel output stage (N=16) stays single-CTA.
   const int cta2 = (s.ntile != 16 && use_cta2_default() && !(desc_variant & 32)) ? 1 : 0;
@@ -406,7 +415,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.total_tiles = p.positions;
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = EPI_RELU6 | (bf16 ? EPI_BF16 : 0);
-    p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo;
+    p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = 6;
     p.out_frame_stride = (long long)Ho * Wo * s.cout;
     L->cta2 = 0;
     L->map_w = L->map;
@@ -467,6 +476,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.a_stages = st; p.w_stages = st; p.w_resident = 0;
   }
   p.desc_variant = desc_variant;
+  static const int no_skip_pf = [] { const char* e = getenv("BSVD_B200_NO_SKIP_PF"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (no_skip_pf) p.desc_variant |= 256;   // debug: no L2 warm-up of the skip operand
   p.wpack = sd.wpack;
   p.bias = sd.bias;
   int flags = 0;
@@ -483,6 +494,10 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (s.pixshuf) { p.out_C = s.cout / 4; p.out_H = 2 * Ho; p.out_W = 2 * Wo; }
   else { p.out_C = s.final_out ? 3 : s.cout; p.out_H = Ho; p.out_W = Wo; }
   p.out_frame_stride = (long long)p.out_H * p.out_W * p.out_C;
+  p.out_C_log2 = 0;
+  while ((1 << p.out_C_log2) < p.out_C) ++p.out_C_log2;
+  if ((1 << p.out_C_log2) != p.out_C || p.out_C < 32) return fail("output channels must be a power of two >= 32");
+  if (s.skip && io.skip && io.skip_C != p.out_C) return fail("skip tensor must have the output's channel count");
   p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
   p.resid_in = io.resid_in; p.resid_C = io.resid_C; p.aux_out = io.aux_out;
   p.fold = p.out_C / 8;
@@ -569,6 +584,7 @@ static int upload_stage(StageDev& sd, const float* w, const float* b, int bf16) 
   if (!sd.bias) CUDA_TRY(cudaMalloc((void**)&sd.bias, bias.size() * 4));
   CUDA_TRY(cudaMemcpy(sd.wpack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(sd.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  sd.bias_h = bias;
   sd.loaded = true;
   return 0;
 }
@@ -1171,7 +1187,7 @@ int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, con
   const int Co = s.pixshuf ? s.cout / 4 : s.cout;
   io.skip = skip; io.skip_C = Co; io.skip_frame_stride = (long long)Ho * Wo * Co;
   StageLaunch L;
-  int rc = plan_stage(sd, io, bf16, d->debug_variant & 0xff, &L);
+  int rc = plan_stage(sd, io, bf16, (d->debug_variant & 0xff) | ((d->debug_variant & (1 << 21)) ? 256 : 0), &L);
   const int a_over = (d->debug_variant >> 8) & 0xf;
   if (!rc && a_over) {   // debug: override the number of A stages (smem permitting)
     L.smem += (size_t)(a_over - L.p.a_stages) * L.p.a_stage_bytes;

@@ -75,10 +75,14 @@ struct ConvParams {
   int w_resident;
   int desc_variant;     // 0 production; debug bits: 2 skip MMA issue, 4 skip epilogue stores,
                         // 8 tap offsets forced to 0 (aligned A), 16 no TMA loads at all,
-                        // 64 no skip loads, 128 no global stores
+                        // 64 no skip loads, 128 no global stores, 256 no L2 prefetch of the skip operand
   // ---- operands ----
   const void* wpack;    // [n_tile][chunk][tap][NTILE][64] 16-bit, rows pre-swizzled (SW128)
   const float* bias;    // [GEMM N]
+  // the same bias values inside the kernel-parameter (constant) bank: the epilogue reads them with
+  // constant loads instead of shared-memory loads, which compete with tcgen05.mma operand reads for
+  // the shared-memory data pipe (ncu: 8 of the 16 LDS/STS per epilogue unit were bias reads)
+  float bias_c[kMaxBias];
   // ---- epilogue ----
   int flags;
   void* out;            // 16-bit NHWC, or fp32 NCHW for EPI_FINAL
@@ -86,6 +90,7 @@ struct ConvParams {
   void* out_next;
   int ring_mode;        // 1 = use out_prev/out_next pointers (T must be 1)
   int out_C, out_H, out_W;
+  int out_C_log2;       // out_C is a power of two: PixelShuffle column -> (sub-pixel, channel) by shift/mask
   long long out_frame_stride;   // elements
   const void* skip;     // 16-bit NHWC with the output's shape (EPI_SKIP) / temp1 output (EPI_FINAL)
   long long skip_frame_stride;
@@ -177,6 +182,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// Asynchronous L2 warm-up of a contiguous global range (no registers, no shared memory, no
+// completion tracking): used for the skip-add operand, which was written a dozen stages earlier and
+// would otherwise be fetched from DRAM on the epilogue's critical path.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                          uint32_t idesc, uint32_t accumulate) {
@@ -400,53 +411,83 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
-  int flags, T, H, W, out_C, out_W, fold, ring_mode, skip_C, resid_C, desc_variant;
+  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant;
   void* out; void* out_prev; void* out_next; void* aux_out;
   const void* skip; const float* resid_in;
   long long out_frame_stride, skip_frame_stride;
   __device__ __forceinline__ explicit EpiParams(const ConvParams& p)
-      : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W), fold(p.fold),
+      : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
+        out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
 };
 
+// Where one epilogue unit (32 GEMM columns x 32 pixels of one image row) lives in the output / skip
+// tensor.  Everything here is warp-uniform (the compiler keeps it in uniform registers): a unit's 32
+// columns share one PixelShuffle sub-pixel q because out_C is a power of two >= 32.
+struct UnitPos {
+  long long base;   // element offset inside a frame of (pixel 0 of the warp's quadrant, channel cb)
+  int cb;           // first output channel of the unit
+};
 template <int MASK, class P>
-__device__ __forceinline__ void skip_prefetch(const P& p, const TileCoord& tc, int y,
+__device__ __forceinline__ UnitPos unit_pos(const P& p, const TileCoord& tc, int y, int nbase, int quad) {
+  UnitPos u;
+  const int xb = tc.x0 + quad * 32;
+  if (((MASK & EPI_PIXSHUF) != 0) && (p.flags & EPI_PIXSHUF)) {
+    const int q = nbase >> p.out_C_log2;
+    u.cb = nbase & (p.out_C - 1);
+    u.base = (static_cast<long long>(2 * y + (q >> 1)) * p.out_W + 2 * xb + (q & 1)) * p.out_C + u.cb;
+  } else {
+    u.cb = nbase;
+    u.base = (static_cast<long long>(y) * p.out_W + xb) * p.out_C + u.cb;
+  }
+  return u;
+}
+// Per-lane constants of the coalesced access pattern shared by the skip fetch and the store phase:
+// lane = (pixel group lane>>2, 16-byte chunk lane&3), so four lanes cover the 64 contiguous bytes
+// of one pixel; a lane serves pixels (lane>>2) + 8 i, i = 0..3.
+struct EpiLane {
+  uint32_t off;     // element offset of (pixel lane>>2, chunk lane&3) relative to UnitPos::base
+  uint32_t step;    // element stride between a lane's four pixels
+  int nvalid;       // valid pixels of the warp's quadrant in this tile (<= 0: none); per tile
+};
+template <int MASK, class P>
+__device__ __forceinline__ EpiLane epi_lane(const P& p, int lane) {
+  EpiLane l;
+  const bool ps = ((MASK & EPI_PIXSHUF) != 0) && (p.flags & EPI_PIXSHUF);
+  l.off = static_cast<uint32_t>((ps ? 2 : 1) * (lane >> 2) * p.out_C + 8 * (lane & 3));
+  l.step = static_cast<uint32_t>((ps ? 16 : 8) * p.out_C);
+  l.nvalid = 0;
+  return l;
+}
+
+// Skip-tensor operand of one unit: 64 contiguous bytes per pixel at the (PixelShuffle-scattered)
+// output location.  Issued one unit ahead of its use so the L2 round trip overlaps the arithmetic
+// of the previous unit.  (The skip tensor has the output's shape: skip_C == out_C.)
+template <int MASK, class P>
+__device__ __forceinline__ void skip_prefetch(const P& p, const TileCoord& tc, const EpiLane& el, int y,
                                               int nbase, int quad, int lane, uint4 (&sk)[4]) {
-  // Coalesced layout (same as the store phase): lane = (pixel group lane>>2, 16-byte chunk lane&3),
-  // so four lanes fetch the 64 contiguous bytes of one pixel: full sectors, 8 lines per request.
   if constexpr ((MASK & EPI_SKIP) != 0) {
     if ((p.flags & EPI_SKIP) && tc.t < p.T && y < p.H && !(p.desc_variant & 64)) {
-      const int j = lane & 3;
-      const int n0 = nbase + 8 * j;
-      int c0 = n0, q = 0;
-      const bool ps = (p.flags & EPI_PIXSHUF) != 0;
-      if (ps) {
-        q = n0 / p.out_C;
-        c0 = n0 - q * p.out_C;
-      }
-      const int oy = ps ? 2 * y + (q >> 1) : y;
-      const int xl = tc.x0 + quad * 32 + (lane >> 2);
-      const int ox0 = ps ? 2 * xl + (q & 1) : xl;
-      const uint16_t* src = reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride +
-                            (static_cast<long long>(oy) * p.out_W + ox0) * p.skip_C + c0;
-      const int step = (ps ? 16 : 8) * p.skip_C;
+      const UnitPos up = unit_pos<MASK>(p, tc, y, nbase, quad);
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(p.skip) + tc.t * p.skip_frame_stride + up.base + el.off;
+      const int pg = lane >> 2;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (xl + 8 * i < p.W) sk[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * step));
+        if (pg + 8 * i < el.nvalid) sk[i] = __ldg(reinterpret_cast<const uint4*>(src + i * el.step));
     }
   }
 }
 
 // MASK = set of EPI_* features compiled into this instance (runtime flags are a subset of it).
 template <bool BF16, int MASK, class P>
-__device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, int y,
+__device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, const EpiLane& el, int y,
                                               int nbase, const uint32_t (&v)[32],
                                               const uint4 (&sk)[4],
-                                              const float* bias_s, uint32_t stg, int quad,
-                                              int lane) {
+                                              const float (&bv)[32], uint32_t stg, int quad,
+                                              int lane, const float (&rin)[3], bool use_rin) {
   const int flags = p.flags & MASK;
   // ------------------------------ phase 0 ------------------------------
   // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
@@ -467,8 +508,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, i
   // (shared-memory accesses are batched: all loads of a phase are issued before their first use)
   {
     const int x = tc.x0 + quad * 32 + lane;
-    const bool valid = (x < p.W) && (y < p.H);
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s + nbase);
+    const bool valid = (lane < el.nvalid) && (y < p.H);
     const uint32_t row = stg + lane * 64;
     const uint32_t swz = (lane >> 1) & 3;
     uint4 sv[4];
@@ -487,11 +527,8 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, i
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float f[8];
-      const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
-      f[0] = __uint_as_float(v[8 * j + 0]) + ba.x; f[1] = __uint_as_float(v[8 * j + 1]) + ba.y;
-      f[2] = __uint_as_float(v[8 * j + 2]) + ba.z; f[3] = __uint_as_float(v[8 * j + 3]) + ba.w;
-      f[4] = __uint_as_float(v[8 * j + 4]) + bb.x; f[5] = __uint_as_float(v[8 * j + 5]) + bb.y;
-      f[6] = __uint_as_float(v[8 * j + 6]) + bb.z; f[7] = __uint_as_float(v[8 * j + 7]) + bb.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) + bv[8 * j + i];
       if constexpr ((MASK & EPI_SKIP) != 0) {
         if (add_skip) {
           const float2 a = unpack2<BF16>(sv[j].x), b = unpack2<BF16>(sv[j].y),
@@ -503,11 +540,16 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, i
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
         if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid) {
           // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
-          const long long plane = static_cast<long long>(p.H) * p.W;
-          const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
-                           static_cast<long long>(y) * p.W + x;
+          if (use_rin) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+            for (int i = 0; i < 3; ++i) f[i] = rin[i] - f[i];
+          } else {
+            const long long plane = static_cast<long long>(p.H) * p.W;
+            const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
+                             static_cast<long long>(y) * p.W + x;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+          }
         }
       }
       o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
@@ -532,21 +574,15 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, i
   // ------------------------------ phase 2 ------------------------------
   {
     const int j = lane & 3;
-    const int n0 = nbase + 8 * j;
-    int c0 = n0, q = 0;
-    if constexpr ((MASK & EPI_PIXSHUF) != 0) {
-      if (flags & EPI_PIXSHUF) {
-        q = n0 / p.out_C;
-        c0 = n0 - q * p.out_C;
-      }
-    }
+    const UnitPos up = unit_pos<MASK>(p, tc, y, nbase, quad);
     // fold routing of this 8-channel group (ShiftConv.forward, bsvd_arch.py:42-50): the consumer
     // conv of frame u reads channels [0,f) of frame u+1 and [f,2f) of frame u-1, so the producer
     // of frame t stores those folds straight into the tensors of frames t-1 / t+1.
     uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + tc.t * p.out_frame_stride;
     uint16_t* zdst = nullptr;       // own-frame location that must read as zero (clip ends)
     if constexpr ((MASK & EPI_SHIFT) != 0) {
-      if (flags & EPI_SHIFT) {
+      if ((flags & EPI_SHIFT) && up.cb < 2 * p.fold) {     // (uniform) only the unit holding the folds
+        const int c0 = up.cb + 8 * j;
         uint16_t* own = dst;
         if (c0 < p.fold) {
           if (p.ring_mode) {
@@ -567,30 +603,28 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, i
         }
       }
     }
-    const bool ps = ((MASK & EPI_PIXSHUF) != 0) && (flags & EPI_PIXSHUF);
-    const int oy = ps ? 2 * y + (q >> 1) : y;
-    const int xl = tc.x0 + quad * 32 + (lane >> 2);          // x of this lane's pixel for i == 0
-    // element offset of (oy, x(i), c0): off0 + i * step
-    const int ox0 = ps ? 2 * xl + (q & 1) : xl;
-    const long long off0 = (static_cast<long long>(oy) * p.out_W + ox0) * p.out_C + c0;
-    const int step = (ps ? 16 : 8) * p.out_C;
-    const bool row_ok = y < p.H;
-    const uint32_t a0 = stg + (lane >> 2) * 64;
+    const long long off0 = up.base + el.off;
+    const bool row_ok = (y < p.H) && !(p.desc_variant & 128);
+    const int pg = lane >> 2;
+    const uint32_t a0 = stg + pg * 64;
     uint4 o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int pl = 8 * i + (lane >> 2);
+      const int pl = 8 * i + pg;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(o[i].x), "=r"(o[i].y), "=r"(o[i].z), "=r"(o[i].w)
                    : "r"(a0 + i * 512 + ((j ^ ((pl >> 1) & 3)) << 4)) : "memory");
     }
+    if (dst) dst += off0;
+    if constexpr ((MASK & EPI_SHIFT) != 0) {
+      if (zdst) zdst += off0;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (row_ok && xl + 8 * i < p.W && !(p.desc_variant & 128)) {
-        const long long off = off0 + static_cast<long long>(i) * step;
-        if (dst) *reinterpret_cast<uint4*>(dst + off) = o[i];
+      if (row_ok && pg + 8 * i < el.nvalid) {
+        if (dst) *reinterpret_cast<uint4*>(dst + i * el.step) = o[i];
         if constexpr ((MASK & EPI_SHIFT) != 0) {
-          if (zdst) *reinterpret_cast<uint4*>(zdst + off) = make_uint4(0, 0, 0, 0);
+          if (zdst) *reinterpret_cast<uint4*>(zdst + i * el.step) = make_uint4(0, 0, 0, 0);
         }
       }
     }
@@ -615,7 +649,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
-  __shared__ __align__(16) float bias_s[kMaxBias];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -651,7 +684,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_tiles * NTILE; i += 64 + 32 * EW) bias_s[i] = p.bias[i];
   if (warp == 1) {
     if constexpr (CTA2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -696,6 +728,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       bool first = true;
       for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
+        if constexpr ((MASK & EPI_SKIP) != 0 && (MASK & EPI_PIXSHUF) != 0) {
+          // Skip operand of THIS tile (consumed by the epilogue about one tile-time from now): with
+          // PixelShuffle the n-tile's sub-pixels q cover whole runs of 2*128 output pixels in output
+          // rows 2y + (q>>1), i.e. one or two contiguous ranges per tile row.
+          if ((p.flags & EPI_SKIP) && (p.flags & EPI_PIXSHUF) && !(p.desc_variant & 256) && tc.t < p.T) {
+            const int nq = (NTILE >= p.out_C) ? NTILE / p.out_C : 1;
+            const int q0 = (tc.nt * NTILE) / p.out_C;
+            const int oy_lo = q0 >> 1, oy_hi = (q0 + nq - 1) >> 1;
+            const int npx = min(2 * kRunPx, p.out_W - 2 * tc.x0);
+            const uint32_t bytes = static_cast<uint32_t>(npx) * p.skip_C * 2u;
+            const uint8_t* sbase = reinterpret_cast<const uint8_t*>(p.skip) +
+                                   2 * (tc.t * p.skip_frame_stride + static_cast<long long>(2 * tc.x0) * p.skip_C);
+            for (int r = 0; r < R && tc.y0 + r < p.H; ++r)
+              for (int o = oy_lo; o <= oy_hi; ++o) {
+                const uint8_t* src = sbase + 2ll * (static_cast<long long>(2 * (tc.y0 + r) + o) * p.out_W) * p.skip_C;
+                for (uint32_t off = 0; off < bytes; off += 16384u)
+                  l2_prefetch_bulk(src + off, min(16384u, bytes - off));
+              }
+          }
+        }
         for (int c = 0; c < p.cin_chunks; ++c) {
           if (p.mode != 1) {
             mbar_wait(a_empty(sa), pa ^ 1);
@@ -873,14 +925,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ======================================= epilogue =======================================
-    const int ew = warp - 2;                   // 0..7
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so everything derived
+    // from it (unit index, bias offset) lives in uniform registers / uniform constant loads
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int ew = warp_u - 2;                 // 0..7
+    const int quad = warp_u & 3;               // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                  // EW/4 warps share a TMEM lane quadrant and split the units
     const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     // register copy of the epilogue parameters, except in the register-starved general instance
-    using EP = typename std::conditional<(MASK & EPI_SKIP) != 0, const ConvParams&, const EpiParams>::type;
-    EP e(p);
+    const EpiParams e(p);
+    EpiLane el = epi_lane<MASK>(e, lane);
     uint32_t it = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
@@ -893,10 +948,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       static_assert(kMine >= 1 && kMine * (EW / 4) == kUnits, "units must split evenly over the warps of a quadrant");
       const int u0 = half * kMine;
       const int nb0 = tc.nt * NTILE;           // global GEMM column of this tile's first column
+      el.nvalid = (tc.t < e.T) ? min(32, e.W - (tc.x0 + quad * 32)) : 0;
       // skip operand of the first unit: issued before waiting for the accumulator, so its latency
       // is covered by the MMAs of this very tile; later units are prefetched one unit ahead
       uint4 ska[4] = {}, skb[4] = {};
-      skip_prefetch<MASK>(e, tc, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
+      skip_prefetch<MASK>(e, tc, el, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
+      // temp1 residual operand (raw fp32 network input, channels 0..2) of this warp's first unit:
+      // fetched while the tile's MMAs are still running instead of on the epilogue's critical path
+      float rin[3] = {0.f, 0.f, 0.f};
+      bool rin_ok = false;
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        if ((e.flags & EPI_RESID_IN) && nb0 + (u0 % G) * 32 == 0) {
+          const int y = tc.y0 + u0 / G, x = tc.x0 + quad * 32 + lane;
+          rin_ok = true;
+          if (tc.t < e.T && y < e.H && x < e.W) {
+            const long long plane = static_cast<long long>(e.H) * e.W;
+            const float* r = e.resid_in + (static_cast<long long>(tc.t) * e.resid_C) * plane +
+                             static_cast<long long>(y) * e.W + x;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rin[i] = __ldg(r + i * plane);
+          }
+        }
+      }
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
@@ -924,13 +997,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (k + 1 < kMine) {
           const int u = u0 + k + 1;
           tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, vb);
-          skip_prefetch<MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
+          skip_prefetch<MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, skb);
         } else {
           release_acc();
         }
         if (work) {
           const int u = u0 + k;
-          epilogue_unit<BF16, MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bias_s, stg, quad, lane);
+          float bv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[nb0 + (u % G) * 32 + i];
+          epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bv, stg, quad, lane,
+                                    rin, k == 0 && rin_ok);
         }
         if (k + 1 < kMine) {
           tmem_ld_wait();
@@ -938,13 +1015,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (k + 2 < kMine) {
             const int u = u0 + k + 2;
             tmem_ld32(tacc + (u / G) * NTILE + (u % G) * 32, va);
-            skip_prefetch<MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
+            skip_prefetch<MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, quad, lane, ska);
           } else {
             release_acc();
           }
           if (work) {
             const int u = u0 + k + 1;
-            epilogue_unit<BF16, MASK>(e, tc, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bias_s, stg, quad, lane);
+            float bv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[nb0 + (u % G) * 32 + i];
+            epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bv, stg, quad, lane,
+                                      rin, false);
           }
         }
       }

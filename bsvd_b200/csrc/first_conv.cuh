@@ -31,7 +31,6 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   constexpr int kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kFirstStages + 5];
-  __shared__ __align__(16) float bias_s[NT];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -58,7 +57,6 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < NT) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   // K slots 36..63 of every patch row are zero for the whole kernel: clear the stages once
   for (uint32_t off = threadIdx.x * 16; off < kFirstStages * kFirstAStage; off += kFirstThreads * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + off), "r"(0) : "memory");
@@ -179,6 +177,8 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile<kFirstR>(p, tile);
+      EpiLane el = epi_lane<EPI_RELU6>(p, lane);
+      el.nvalid = min(32, p.W - (tc.x0 + quad * 32));
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
@@ -186,14 +186,20 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       const int u0 = half * 2;                 // 4 units (2 rows x 2 column groups), 2 per warp half
       uint32_t va[32], vb[32];
       const uint4 nosk[4] = {};
+      const float norin[3] = {};
       tmem_ld32(tacc + (u0 / G) * NT + (u0 % G) * 32, va);
       tmem_ld32(tacc + ((u0 + 1) / G) * NT + ((u0 + 1) % G) * 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
-      epilogue_unit<BF16, EPI_RELU6>(p, tc, tc.y0 + u0 / G, (u0 % G) * 32, va, nosk, bias_s, stg, quad, lane);
-      epilogue_unit<BF16, EPI_RELU6>(p, tc, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bias_s, stg, quad, lane);
+      float bv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[(u0 % G) * 32 + i];
+      epilogue_unit<BF16, EPI_RELU6>(p, tc, el, tc.y0 + u0 / G, (u0 % G) * 32, va, nosk, bv, stg, quad, lane, norin, false);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[((u0 + 1) % G) * 32 + i];
+      epilogue_unit<BF16, EPI_RELU6>(p, tc, el, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bv, stg, quad, lane, norin, false);
     }
   }
   tc_fence_before();

@@ -22,5 +22,23 @@ def run(name, T, H, W, cin, cout, flags, variant=0, a_stages=0, reps=4, w_stages
     by = 2.0 * T * (H * W * cin + Ho * Wo * Co * (2 if flags & K else 1))
     print(f"{name:34s} var={variant} a_st={a_stages} w_st={w_stages}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TF/s  {by/ms/1e6:7.1f} GB/s", flush=True)
 T = 10
-for var in (0, 4, 20, 1 << 20, (1 << 20) | 4, (1 << 20) | 20):
-    run("64->64 full", T, 540, 960, 64, 64, R, var)
+which = sys.argv[1] if len(sys.argv) > 1 else "up1"
+NOPF = 1 << 21
+if which == "64":
+    for var in (0, 4, 20, 1 << 20, (1 << 20) | 4, (1 << 20) | 20):
+        run("64->64 full", T, 540, 960, 64, 64, R, var)
+elif which == "up1":
+    # upc1.convblock.0: 128 -> 256 at half res, PixelShuffle + skip add to full res
+    for var in (0, NOPF, 64, 128, 64 | 128, 4, 2, 16, 2 | 16):
+        run("upc1.conv 128->256 PS+skip", T, 270, 480, 128, 256, P | K, var)
+    for var in (0, 4):
+        run("128->256 PS only", T, 270, 480, 128, 256, P, var)
+        run("128->256 plain", T, 270, 480, 128, 256, 0, var)
+elif which == "up2":
+    for var in (0, NOPF, 64, 128, 4, 2):
+        run("upc2.conv 256->512 PS+skip+shift", T, 135, 240, 256, 512, P | K | S, var)
+elif which == "s2":
+    for var in (0, 4, 2, 16):
+        run("downc0.conv 64->128 s2 shift", T, 540, 960, 64, 128, R | D | S, var)
+    for var in (0, 4, 2, 16):
+        run("downc1.conv 128->256 s2 shift", T, 270, 480, 128, 256, R | D | S, var)
