@@ -93,6 +93,26 @@ static int make_map_s2(CUtensorMap* m, const void* base, int T, int H, int W, in
   return 0;
 }
 
+// [T][Ho][Wo][C] seen as [T][Ho][Wo/2][2*C] (PixelShuffle: the two sub-pixel columns of a source pixel
+// are adjacent in memory), or as is (ps = 0).  box_c x box_px elements per box; `swz` 128 B for MMA
+// operands (skip blocks [128 px][64 ch]), 64 B for epilogue units ([32 px][32 ch] TMA stores).
+// T may be a ring of slots with its own stride (streaming mode).
+static int make_map_pix(CUtensorMap* m, const void* base, int T, long long t_stride_bytes, int Ho, int Wo,
+                        int C, int ps, int box_c, int box_px, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  const int cw = ps ? 2 * C : C, wp = ps ? Wo / 2 : Wo;
+  cuuint64_t dims[4] = {(cuuint64_t)cw, (cuuint64_t)wp, (cuuint64_t)Ho, (cuuint64_t)T};
+  cuuint64_t strides[3] = {(cuuint64_t)cw * 2, (cuuint64_t)Wo * C * 2, (cuuint64_t)t_stride_bytes};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_px, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(pixel view) failed: %d", (int)r);
+  return 0;
+}
+
 // Packed weights as a 2-D tensor [rows][64] (rows of 128 B, already swizzled by the host): the CTA-pair
 // kernels fetch half of a filter slab per CTA with a TMA that can signal the leader CTA's barrier.
 static int make_map_w(CUtensorMap* m, const void* base, size_t rows, int box_rows) {
@@ -279,6 +299,9 @@ struct StageIO {
   const float* resid_in = nullptr;
   int resid_C = 0;
   void* aux_out = nullptr;
+  // streaming: `skip` / `out` are ring bases of skip_T / out_T slots (0 = plain [T] tensors)
+  int skip_T = 0, out_T = 0;
+  long long skip_T_stride = 0, out_T_stride = 0;   // bytes
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -292,6 +315,8 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st);
 struct StageLaunch {
   CUtensorMap map;      // activations
   CUtensorMap map_w;    // packed weights (CTA-pair kernels)
+  CUtensorMap map_s;    // skip tensor, PixelShuffle view (skip add on the tensor core)
+  CUtensorMap map_o;    // output tensor (TMA stores)
   ConvParams p;
   int grid = 0;
   size_t smem = 0;
@@ -331,7 +356,7 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.map_s, L.map_o, L.p));
   return 0;
 }
 // Epilogue feature sets the kernels are specialised for; a stage runs on the smallest set that
@@ -339,8 +364,10 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
 constexpr int kMaskPlain = EPI_RELU6;
 constexpr int kMaskShift = EPI_RELU6 | EPI_SHIFT;
 constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
-constexpr int kMaskUp = EPI_PIXSHUF | EPI_SKIP;                  // upc1.convblock.0
-constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0
+// PixelShuffle stages: the skip add runs on the tensor core (ConvParams::skip_mma), so the
+// epilogue instances carry no skip path
+constexpr int kMaskUpTma = EPI_PIXSHUF | EPI_TMA_OUT;   // upc1.convblock.0: units leave through TMA stores
+constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0: fold routing at the store
 constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
@@ -350,8 +377,8 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
     if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
     if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
-    if constexpr (NTILE == 256) {
-      if ((f & ~kMaskUp) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUp, 8>(L, st);
+    if constexpr (NTILE == 256 && R == 1) {
+      if (L.p.tma_out && (f & ~kMaskUpTma) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpTma, 8>(L, st);
       if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpShift, 8>(L, st);
     }
   }
@@ -398,7 +425,15 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   // 8 epilogue warps: 16 were measured (kernel template parameter EW) and bring nothing — the
   // gap between a full stage and its epilogue-less run is shared-memory/L2 contention, not latency
   L->ew = 8;
-  const size_t kStagingBytes = staging_bytes(L->ew);
+  // PixelShuffle + skip stages on the CTA-pair <256,1> kernel: the skip tensor is accumulated by an
+  // identity MMA (TMA-loaded like an extra K chunk); without a temporal shift on the output the
+  // epilogue units also leave through TMA stores (double-buffered staging).
+  static const int up_on = [] { const char* e = getenv("BSVD_B200_NO_SKIP_MMA"); return (e && e[0] == '1') ? 0 : 1; }();
+  const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
+                        !s.first_im2col && !s.final_out;
+  static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
+  const bool tma_out = tma_on && skip_mma && !s.shift && !s.relu6;
+  const size_t kStagingBytes = staging_bytes(L->ew) * (tma_out ? 2 : 1) + (skip_mma ? 4096 : 0);
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;
@@ -483,7 +518,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   int flags = 0;
   if (s.relu6) flags |= EPI_RELU6;
   if (s.pixshuf) flags |= EPI_PIXSHUF;
-  if (s.skip) flags |= EPI_SKIP;
+  if (s.skip && !skip_mma) flags |= EPI_SKIP;
   if (s.shift) flags |= EPI_SHIFT;
   if (s.resid_in) flags |= EPI_RESID_IN;
   if (s.final_out) flags |= EPI_FINAL;
@@ -501,6 +536,9 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
   p.resid_in = io.resid_in; p.resid_C = io.resid_C; p.aux_out = io.aux_out;
   p.fold = p.out_C / 8;
+  p.stg_bytes_per_warp = kStageBytesPerWarp * (tma_out ? 2 : 1);
+  p.skip_mma = skip_mma ? s.ntile / 64 : 0;
+  p.tma_out = tma_out ? 1 : 0;
   if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
 
@@ -513,6 +551,20 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     if (rc) return rc;
   } else {
     L->map_w = L->map;   // unused
+  }
+  L->map_s = L->map; L->map_o = L->map;   // unused unless set below
+  const long long frame_bytes = p.out_frame_stride * 2;
+  if (skip_mma) {
+    if (p.a_stage_bytes < 2u * 16384u) return fail("A stage too small for two skip blocks");
+    rc = make_map_pix(&L->map_s, io.skip, io.skip_T ? io.skip_T : io.T,
+                      io.skip_T ? io.skip_T_stride : frame_bytes, p.out_H, p.out_W, p.out_C, 1, kChunk,
+                      kRunPx, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (tma_out) {
+    rc = make_map_pix(&L->map_o, io.out, io.out_T ? io.out_T : io.T, io.out_T ? io.out_T_stride : frame_bytes,
+                      p.out_H, p.out_W, p.out_C, s.pixshuf ? 1 : 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
   }
   L->grid = cta2 ? 2 * std::min(p.total_tiles, num_sms() / 2) : std::min(p.total_tiles, num_sms());
   L->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.w_stages * p.w_stage_bytes +
@@ -1061,7 +1113,12 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       io.out_next = io.out;                      // placeholders so plan_stage's checks pass
       io.skip = S.ring[b][kRingX0]; io.skip_C = 64;
       io.resid_in = S.raw; io.resid_C = 4;
-      if (l == 10) { io.skip = S.ring[b][kRingX1]; io.skip_C = 128; }
+      io.skip_T = kRingSlots[kRingX0]; io.skip_T_stride = (long long)ring_slot_bytes(kRingX0, H, W);
+      if (l == 10) {
+        io.skip = S.ring[b][kRingX1]; io.skip_C = 128;
+        io.skip_T = kRingSlots[kRingX1]; io.skip_T_stride = (long long)ring_slot_bytes(kRingX1, H, W);
+      }
+      io.out_T = kRingSlots[kLayerOut[l]]; io.out_T_stride = (long long)ring_slot_bytes(kLayerOut[l], H, W);
       if (l == 15 && b == 1) { io.skip = S.aux; io.skip_C = 4; }
       if (l == 15 && b == 0) io.aux_out = S.aux;
       if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
@@ -1125,8 +1182,15 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
         p.out_prev = (f > 0) ? oslot(f - 1) : nullptr;
         p.out_next = oslot(f + 1);
       }
-      if (l == 10) p.skip = S.ring[b][kRingX1] + (size_t)(f % kRingSlots[kRingX1]) * ring_slot_bytes(kRingX1, H, W);
-      if (l == 13) p.skip = S.ring[b][kRingX0] + (size_t)(f % kRingSlots[kRingX0]) * ring_slot_bytes(kRingX0, H, W);
+      p.out_t0 = (int)(f % kRingSlots[oring]);     // TMA stores address the ring through map_o
+      if (l == 10) {
+        p.skip_t0 = (int)(f % kRingSlots[kRingX1]);   // skip add on the tensor core: ring slot of map_s
+        p.skip = S.ring[b][kRingX1] + (size_t)p.skip_t0 * ring_slot_bytes(kRingX1, H, W);
+      }
+      if (l == 13) {
+        p.skip_t0 = (int)(f % kRingSlots[kRingX0]);
+        p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(kRingX0, H, W);
+      }
       const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
       if (l == 0 && b == 0) {
         L.first_in = S.raw + (size_t)(f % 9) * 4 * plane;   // raw ring slot holds all 4 channels

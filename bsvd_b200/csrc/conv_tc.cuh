@@ -52,7 +52,8 @@ enum : int {
   EPI_RESID_IN = 16,    // temp1 outc.3: out[:, :3] = raw_in[:, :3] - out[:, :3]
   EPI_FINAL = 32,       // temp2 outc.3 (final_conv.cuh): fp32 NCHW out = skip[:, :3] - conv[:, :3]
   EPI_BF16 = 64,        // 16-bit storage type is bf16 (else fp16)
-  EPI_ZERO_FUTURE = 128 // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
+  EPI_ZERO_FUTURE = 128, // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
+  EPI_TMA_OUT = 256     // compile-time only: units leave through cp.async.bulk.tensor stores
 };
 
 struct ConvParams {
@@ -75,7 +76,7 @@ struct ConvParams {
   int w_resident;
   int desc_variant;     // 0 production; debug bits: 2 skip MMA issue, 4 skip epilogue stores,
                         // 8 tap offsets forced to 0 (aligned A), 16 no TMA loads at all,
-                        // 64 no skip loads, 128 no global stores, 256 no L2 prefetch of the skip operand
+                        // 64 no skip loads, 128 no global stores
   // ---- operands ----
   const void* wpack;    // [n_tile][chunk][tap][NTILE][64] 16-bit, rows pre-swizzled (SW128)
   const float* bias;    // [GEMM N]
@@ -100,6 +101,12 @@ struct ConvParams {
   void* aux_out;        // EPI_RESID_IN: compact 16-bit [T][H][W][4] copy of output channels 0..3
                         // (the skip1 operand of temp2's residual: 8 B/px instead of a 128 B row)
   int fold;             // shift fold size in output channels (EPI_SHIFT)
+  // ---- skip add on the tensor core / TMA stores (CTA-pair kernels, see conv3x3_tc_kernel) ----
+  int skip_mma;         // > 0: number of 64-column blocks per tile whose skip operand is accumulated
+                        // by an identity MMA (PixelShuffle + skip stages); the epilogue sees no skip
+  int tma_out;          // 1: the epilogue stores its units with TMA (EPI_TMA_OUT instances)
+  int skip_t0, out_t0;  // frame coordinate offsets into map_s / map_o (streaming: ring slot)
+  uint32_t stg_bytes_per_warp;   // epilogue staging per warp: 2 KB, or 4 KB (double-buffered) with TMA stores
 };
 
 // --------------------------------------------------------------------------------------------
@@ -183,11 +190,23 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-// Asynchronous L2 warm-up of a contiguous global range (no registers, no shared memory, no
-// completion tracking): used for the skip-add operand, which was written a dozen stages earlier and
-// would otherwise be fetched from DRAM on the epilogue's critical path.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+// TMA store of one epilogue unit: shared memory [32 px][32 ch] (SWIZZLE_64B) -> global tensor.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                          uint32_t idesc, uint32_t accumulate) {
@@ -411,7 +430,7 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
-  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant;
+  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0;
   void* out; void* out_prev; void* out_next; void* aux_out;
   const void* skip; const float* resid_in;
   long long out_frame_stride, skip_frame_stride;
@@ -419,6 +438,7 @@ struct EpiParams {
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
+        out_t0(p.out_t0),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
@@ -487,8 +507,14 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
                                               int nbase, const uint32_t (&v)[32],
                                               const uint4 (&sk)[4],
                                               const float (&bv)[32], uint32_t stg, int quad,
-                                              int lane, const float (&rin)[3], bool use_rin) {
+                                              int lane, const float (&rin)[3], bool use_rin,
+                                              const CUtensorMap* map_o = nullptr) {
   const int flags = p.flags & MASK;
+  if constexpr ((MASK & EPI_TMA_OUT) != 0) {
+    // the TMA store that last read this staging buffer (two units ago) must have drained it
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+  }
   // ------------------------------ phase 0 ------------------------------
   // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
   if constexpr ((MASK & EPI_SKIP) != 0) {
@@ -570,6 +596,26 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ swz) << 4)),
                    "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w) : "memory");
   }
+  if constexpr ((MASK & EPI_TMA_OUT) != 0) {
+    // ------------------------------ phase 2 (TMA) ------------------------------
+    // The staging tile [32 px][64 B] with its XOR pattern IS the SWIZZLE_64B box layout: one
+    // cp.async.bulk.tensor store moves the unit; the tensor map clips pixels beyond the image.
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (el.nvalid > 0 && !(p.desc_variant & 128)) {
+        int c0 = nbase, c2 = y;
+        if (p.flags & EPI_PIXSHUF) {
+          const int q = nbase >> p.out_C_log2;
+          c0 = (q & 1) * p.out_C + (nbase & (p.out_C - 1));
+          c2 = 2 * y + (q >> 1);
+        }
+        tma_store_4d(map_o, stg, c0, tc.x0 + quad * 32, c2, tc.t + p.out_t0);
+      }
+      bulk_commit_group();      // one group per unit, empty or not: keeps the wait_group count exact
+    }
+    return;
+  }
   __syncwarp();
   // ------------------------------ phase 2 ------------------------------
   {
@@ -638,6 +684,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o,
                   const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
   constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator set
@@ -662,6 +709,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t a_base = smem_base;
   const uint32_t w_base = a_base + p.a_stages * p.a_stage_bytes;
   const uint32_t stg_base = w_base + p.w_stages * p.w_stage_bytes;
+  const uint32_t id_base = stg_base + EW * p.stg_bytes_per_warp;   // 64x64 identity (skip_mma), 4 KB per CTA
 
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
@@ -693,6 +741,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                    ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  if constexpr (CTA2 && R == 1) {
+    if (p.skip_mma) {
+      // This CTA's half of the 64x64 identity B operand (N rows [32 rank, +32), K-major, SW128):
+      // the skip tensor goes through the tensor core as D += S * I (exact: 16-bit x 1.0 into fp32).
+      for (int i = threadIdx.x; i < 256; i += 64 + 32 * EW) {
+        const int row = i >> 3, cphys = i & 7;
+        const int n = 32 * static_cast<int>(rank) + row;
+        const uint32_t one = BF16 ? 0x3F80u : 0x3C00u;
+        const bool hit = (cphys ^ (row & 7)) == (n >> 3);
+        const uint32_t v = one << (16 * (n & 1));
+        const int wi = (n & 7) >> 1;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(id_base + i * 16),
+                     "r"((hit && wi == 0) ? v : 0u), "r"((hit && wi == 1) ? v : 0u),
+                     "r"((hit && wi == 2) ? v : 0u), "r"((hit && wi == 3) ? v : 0u) : "memory");
+      }
+      fence_proxy_async();
     }
   }
   tc_fence_before();
@@ -728,26 +794,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       bool first = true;
       for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
-        if constexpr ((MASK & EPI_SKIP) != 0 && (MASK & EPI_PIXSHUF) != 0) {
-          // Skip operand of THIS tile (consumed by the epilogue about one tile-time from now): with
-          // PixelShuffle the n-tile's sub-pixels q cover whole runs of 2*128 output pixels in output
-          // rows 2y + (q>>1), i.e. one or two contiguous ranges per tile row.
-          if ((p.flags & EPI_SKIP) && (p.flags & EPI_PIXSHUF) && !(p.desc_variant & 256) && tc.t < p.T) {
-            const int nq = (NTILE >= p.out_C) ? NTILE / p.out_C : 1;
-            const int q0 = (tc.nt * NTILE) / p.out_C;
-            const int oy_lo = q0 >> 1, oy_hi = (q0 + nq - 1) >> 1;
-            const int npx = min(2 * kRunPx, p.out_W - 2 * tc.x0);
-            const uint32_t bytes = static_cast<uint32_t>(npx) * p.skip_C * 2u;
-            const uint8_t* sbase = reinterpret_cast<const uint8_t*>(p.skip) +
-                                   2 * (tc.t * p.skip_frame_stride + static_cast<long long>(2 * tc.x0) * p.skip_C);
-            for (int r = 0; r < R && tc.y0 + r < p.H; ++r)
-              for (int o = oy_lo; o <= oy_hi; ++o) {
-                const uint8_t* src = sbase + 2ll * (static_cast<long long>(2 * (tc.y0 + r) + o) * p.out_W) * p.skip_C;
-                for (uint32_t off = 0; off < bytes; off += 16384u)
-                  l2_prefetch_bulk(src + off, min(16384u, bytes - off));
-              }
-          }
-        }
         for (int c = 0; c < p.cin_chunks; ++c) {
           if (p.mode != 1) {
             mbar_wait(a_empty(sa), pa ^ 1);
@@ -792,6 +838,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
         }
+        if constexpr (CTA2 && R == 1) {
+          // skip operand of this tile: block bb = GEMM columns [64 bb, +64) = 64 channels of one
+          // sub-pixel; in the [T][2H][W][2][C] view of the skip tensor that is a plain [128 px][64 ch]
+          // box, two of which share one A stage
+          for (int s2 = 0; s2 < p.skip_mma; s2 += 2) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            if (rank == 0) mbar_expect_tx(a_full(sa), 2u * 2u * 16384u);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int n = tc.nt * NTILE + (s2 + b) * 64;
+              const int q = n >> p.out_C_log2, ch = n & (p.out_C - 1);
+              tma_load_4d_2sm(a_base + sa * p.a_stage_bytes + b * 16384u, &map_s, a_full(sa),
+                              (q & 1) * p.out_C + ch, tc.x0, 2 * tc.y0 + (q >> 1), tc.t + p.skip_t0);
+            }
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+          }
+        }
         first = false;
       }
     }
@@ -806,7 +869,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t leader = elect_one();
       constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);  // SW128, version 1, SBO 1024
       const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
-      const bool skip_mma = (p.desc_variant & 2) != 0;
+      const bool no_mma = (p.desc_variant & 2) != 0;
       const bool no_load = (p.desc_variant & 16) != 0;
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       uint32_t it = 0;
@@ -834,7 +897,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kAccCols;
           const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          if (leader && !skip_mma) {
+          if (leader && !no_mma) {
 #pragma unroll
             for (int hr = 0; hr < 4; ++hr) {
               const uint32_t col0 = (hr == 3) ? 64u : 0u;
@@ -881,7 +944,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = (((w_base + sw * p.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t first = (c == 0 && tap == p.tap_begin) ? 0u : 1u;
-            if (leader && !skip_mma) {
+            if (leader && !no_mma) {
 #pragma unroll
               for (int r = 0; r < R; ++r) {
                 const uint32_t a_off = (p.mode == 0 && !(p.desc_variant & 8))
@@ -919,6 +982,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
+        if constexpr (CTA2 && R == 1) {
+          const uint32_t idesc_id = make_idesc(64, BF16 ? 1 : 0, 256);
+          const uint32_t id_lo0 = ((id_base & 0x3FFFFu) >> 4) | (1u << 16);
+          for (int s2 = 0; s2 < p.skip_mma; s2 += 2) {
+            if (!no_load) mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+            const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            if (leader && !no_mma) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_2sm(tmem_acc + (s2 + b) * 64, desc_hi | (a_lo0 + b * (16384u >> 4) + k * 2u),
+                               desc_hi | (id_lo0 + k * 2u), idesc_id, 1u);
+            }
+            if (leader) umma_commit_2sm(a_empty(sa));
+            __syncwarp();
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+          }
+        }
         if (leader) { if constexpr (CTA2) umma_commit_2sm(acc_full(buf)); else umma_commit(acc_full(buf)); }
         __syncwarp();
       }
@@ -931,7 +1014,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int ew = warp_u - 2;                 // 0..7
     const int quad = warp_u & 3;               // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                  // EW/4 warps share a TMEM lane quadrant and split the units
-    const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
+    const uint32_t stg0 = stg_base + ew * p.stg_bytes_per_warp;
+    uint32_t ucount = 0;                       // TMA stores: units alternate between two staging tiles
+    auto next_stg = [&]() -> uint32_t {
+      if constexpr ((MASK & EPI_TMA_OUT) != 0) return stg0 + (ucount++ & 1u) * kStageBytesPerWarp;
+      else return stg0;
+    };
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     // register copy of the epilogue parameters, except in the register-starved general instance
     const EpiParams e(p);
@@ -1006,8 +1094,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           float bv[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[nb0 + (u % G) * 32 + i];
-          epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bv, stg, quad, lane,
-                                    rin, k == 0 && rin_ok);
+          epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, va, ska, bv, next_stg(), quad, lane,
+                                    rin, k == 0 && rin_ok, &map_o);
         }
         if (k + 1 < kMine) {
           tmem_ld_wait();
@@ -1024,11 +1112,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             float bv[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[nb0 + (u % G) * 32 + i];
-            epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bv, stg, quad, lane,
-                                      rin, false);
+            epilogue_unit<BF16, MASK>(e, tc, el, tc.y0 + u / G, nb0 + (u % G) * 32, vb, skb, bv, next_stg(), quad, lane,
+                                      rin, false, &map_o);
           }
         }
       }
+    }
+    if constexpr ((MASK & EPI_TMA_OUT) != 0) {
+      if (lane == 0) bulk_wait_group_all();    // staging must outlive the last TMA reads
+      __syncwarp();
     }
   }
 

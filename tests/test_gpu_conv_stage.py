@@ -26,7 +26,10 @@ CASES = [
     ("256to256_shift", 3, 7, 132, 256, 256, R | S),
     ("256to256_noact", 2, 5, 60, 256, 256, 0),
     ("256to512_ps_skip_shift", 3, 7, 132, 256, 512, P | K | S),
-    ("128to256_ps_skip", 3, 10, 136, 128, 256, P | K),
+    ("128to256_ps_skip", 3, 10, 136, 128, 256, P | K),            # skip on the tensor core + TMA stores
+    ("128to256_ps_skip_wide", 2, 6, 480, 128, 256, P | K),
+    ("64to128_ps_skip_epilogue", 2, 6, 72, 64, 128, P | K),       # skip added in the epilogue (N tile 128)
+    ("128to256_ps_only", 2, 6, 72, 128, 256, P),
     ("tiny_4x4", 2, 4, 4, 64, 64, R),
 ]
 
