@@ -453,7 +453,11 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = 6;
     p.out_frame_stride = (long long)Ho * Wo * s.cout;
     L->cta2 = 0;
-    L->map_w = L->map;
+    if (make_map_pix(&L->map_o, io.out, io.out_T ? io.out_T : io.T,
+                     io.out_T ? io.out_T_stride : p.out_frame_stride * 2, Ho, Wo, s.cout, 0, 32, 32,
+                     CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    p.tma_out = 1; p.stg_bytes_per_warp = 2 * kStageBytesPerWarp;
+    L->map = L->map_o; L->map_w = L->map_o; L->map_s = L->map_o;
     L->grid = std::min(p.total_tiles, num_sms());
     L->smem = kFirstSmem;
     L->ntile = -1; L->rows = kFirstR;
@@ -592,9 +596,9 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (L.p.flags & EPI_BF16)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true>, L.first_in, L.first_nmap, L.first_inc, L.p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p));
   else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false>, L.first_in, L.first_nmap, L.first_inc, L.p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p));
   return 0;
 }
 

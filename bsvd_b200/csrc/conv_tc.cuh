@@ -1025,6 +1025,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const EpiParams e(p);
     EpiLane el = epi_lane<MASK>(e, lane);
     uint32_t it = 0;
+    // temp1 residual operand (raw fp32 network input, channels 0..2) of this warp's first unit,
+    // fetched one whole tile ahead: a first-touch DRAM read takes longer than one tile's MMAs
+    float rin_next[3] = {0.f, 0.f, 0.f};
+    auto load_rin = [&](int tile_idx) {
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        constexpr int G = NTILE / 32;
+        const int u0 = (ew >> 2) * ((R * G) / (EW / 4));
+        if ((e.flags & EPI_RESID_IN) && tile_idx < p.total_tiles) {
+          const TileCoord tn = decode_tile<R>(p, tile_idx, CTA2, rank);
+          const int y = tn.y0 + u0 / G, x = tn.x0 + quad * 32 + lane;
+          if (tn.nt * NTILE + (u0 % G) * 32 == 0 && tn.t < e.T && y < e.H && x < e.W) {
+            const long long plane = static_cast<long long>(e.H) * e.W;
+            const float* r = e.resid_in + (static_cast<long long>(tn.t) * e.resid_C) * plane +
+                             static_cast<long long>(y) * e.W + x;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rin_next[i] = __ldg(r + i * plane);
+          }
+        }
+      }
+    };
+    load_rin(tile0);
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
       const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
       const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
@@ -1041,22 +1062,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // is covered by the MMAs of this very tile; later units are prefetched one unit ahead
       uint4 ska[4] = {}, skb[4] = {};
       skip_prefetch<MASK>(e, tc, el, tc.y0 + u0 / G, nb0 + (u0 % G) * 32, quad, lane, ska);
-      // temp1 residual operand (raw fp32 network input, channels 0..2) of this warp's first unit:
-      // fetched while the tile's MMAs are still running instead of on the epilogue's critical path
-      float rin[3] = {0.f, 0.f, 0.f};
+      float rin[3] = {rin_next[0], rin_next[1], rin_next[2]};
       bool rin_ok = false;
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
-        if ((e.flags & EPI_RESID_IN) && nb0 + (u0 % G) * 32 == 0) {
-          const int y = tc.y0 + u0 / G, x = tc.x0 + quad * 32 + lane;
-          rin_ok = true;
-          if (tc.t < e.T && y < e.H && x < e.W) {
-            const long long plane = static_cast<long long>(e.H) * e.W;
-            const float* r = e.resid_in + (static_cast<long long>(tc.t) * e.resid_C) * plane +
-                             static_cast<long long>(y) * e.W + x;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) rin[i] = __ldg(r + i * plane);
-          }
-        }
+        rin_ok = (e.flags & EPI_RESID_IN) && nb0 + (u0 % G) * 32 == 0;
+        load_rin(tile + tstep);
       }
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();

@@ -20,12 +20,13 @@ constexpr int kFirstProducers = 128;
 constexpr int kFirstStages = 4;
 constexpr uint32_t kFirstAStage = kFirstR * kRunPx * 128;   // 32 KB
 constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
-constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * kStageBytesPerWarp;
+// epilogue staging: two 2 KB tiles per warp (units leave through TMA stores, see conv_tc.cuh)
+constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * 2 * kStageBytesPerWarp;
 
 template <bool BF16>
 __global__ void __launch_bounds__(kFirstThreads, 1)
 first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, int in_c,
-                  const __grid_constant__ ConvParams p) {
+                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p) {
   constexpr int NT = 64;
   constexpr int kAccCols = kFirstR * NT;
   constexpr int kTmemCols = 2 * kAccCols;
@@ -171,7 +172,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     const int ew = warp - 9;                   // 0..7
     const int quad = warp & 3;
     const int half = ew >> 2;
-    const uint32_t stg = stg_base + ew * kStageBytesPerWarp;
+    const uint32_t stg = stg_base + ew * 2 * kStageBytesPerWarp;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int G = NT / 32;
     uint32_t it = 0;
@@ -193,14 +194,17 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      constexpr int kEpiMask = EPI_RELU6 | EPI_TMA_OUT;
       float bv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[(u0 % G) * 32 + i];
-      epilogue_unit<BF16, EPI_RELU6>(p, tc, el, tc.y0 + u0 / G, (u0 % G) * 32, va, nosk, bv, stg, quad, lane, norin, false);
+      epilogue_unit<BF16, kEpiMask>(p, tc, el, tc.y0 + u0 / G, (u0 % G) * 32, va, nosk, bv, stg, quad, lane, norin, false, &map_o);
 #pragma unroll
       for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[((u0 + 1) % G) * 32 + i];
-      epilogue_unit<BF16, EPI_RELU6>(p, tc, el, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bv, stg, quad, lane, norin, false);
+      epilogue_unit<BF16, kEpiMask>(p, tc, el, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bv, stg + kStageBytesPerWarp, quad, lane, norin, false, &map_o);
     }
+    if (lane == 0) bulk_wait_group_all();      // staging must outlive the last TMA reads
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
