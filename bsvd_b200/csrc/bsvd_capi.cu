@@ -367,7 +367,8 @@ constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
 // PixelShuffle stages: the skip add runs on the tensor core (ConvParams::skip_mma), so the
 // epilogue instances carry no skip path
 constexpr int kMaskUpTma = EPI_PIXSHUF | EPI_TMA_OUT;   // upc1.convblock.0: units leave through TMA stores
-constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0: fold routing at the store
+constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0 with the skip on the tensor core (opt-in)
+constexpr int kMaskUpSkipShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0: skip added in the epilogue
 constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
@@ -380,6 +381,7 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
     if constexpr (NTILE == 256 && R == 1) {
       if (L.p.tma_out && (f & ~kMaskUpTma) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpTma, 8>(L, st);
       if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpShift, 8>(L, st);
+      if ((f & ~kMaskUpSkipShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpSkipShift, 8>(L, st);
     }
   }
   return launch_inst<NTILE, R, BF16, true, kMaskAll, 8>(L, st);
@@ -429,8 +431,11 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   // identity MMA (TMA-loaded like an extra K chunk); without a temporal shift on the output the
   // epilogue units also leave through TMA stores (double-buffered staging).
   static const int up_on = [] { const char* e = getenv("BSVD_B200_NO_SKIP_MMA"); return (e && e[0] == '1') ? 0 : 1; }();
+  // (upc2.convblock.0, with its temporal shift, keeps the skip add in the epilogue unless
+  // BSVD_B200_SKIP_MMA_SHIFT=1: its MMA time is the bound, not its epilogue)
+  static const int up_shift_on = [] { const char* e = getenv("BSVD_B200_SKIP_MMA_SHIFT"); return (e && e[0] == '1') ? 1 : 0; }();
   const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
-                        !s.first_im2col && !s.final_out;
+                        !s.first_im2col && !s.final_out && (!s.shift || up_shift_on);
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
   const bool tma_out = tma_on && skip_mma && !s.shift && !s.relu6;
   const size_t kStagingBytes = staging_bytes(L->ew) * (tma_out ? 2 : 1) + (skip_mma ? 4096 : 0);
@@ -559,7 +564,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   L->map_s = L->map; L->map_o = L->map;   // unused unless set below
   const long long frame_bytes = p.out_frame_stride * 2;
   if (skip_mma) {
-    if (p.a_stage_bytes < 2u * 16384u) return fail("A stage too small for two skip blocks");
+    if (p.w_stage_bytes != 16384u || p.w_resident || s.cin_chunks * s.ntaps() < 4 * (s.ntile / 64))
+      return fail("skip blocks need 16 KB filter-ring slots and at least four slabs per block");
     rc = make_map_pix(&L->map_s, io.skip, io.skip_T ? io.skip_T : io.T,
                       io.skip_T ? io.skip_T_stride : frame_bytes, p.out_H, p.out_W, p.out_C, 1, kChunk,
                       kRunPx, CU_TENSOR_MAP_SWIZZLE_128B);

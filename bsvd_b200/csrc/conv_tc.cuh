@@ -782,32 +782,44 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();            // everything above touched only weights/bias; activations come next
 
-  const int ntaps = p.tap_end - p.tap_begin;
+  // Local copy of the pipeline parameters for the producer / MMA loops.  NOTE (measured): forcing these
+  // into general registers (opaque asm) makes every non-stacked stage 15-25 % slower, because the MMA
+  // issue loop then leaves the uniform datapath (R2UR in front of every descriptor); left alone, ptxas
+  // re-materialises them from the constant bank with uniform loads, which is the faster of the two.
+  struct {
+    int a_stages, w_stages, cin_chunks, tap_begin, tap_end, mode, w_resident, total_tiles, desc_variant,
+        skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0;
+    uint32_t a_stage_bytes, w_stage_bytes, a_tx_bytes;
+  } const pp = {p.a_stages, p.w_stages, p.cin_chunks, p.tap_begin, p.tap_end, p.mode, p.w_resident,
+                p.total_tiles, p.desc_variant, p.skip_mma, p.w_rows_cta, p.cin_total, p.out_C_log2, p.out_C,
+                p.skip_t0, p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
+  const int ntaps = pp.tap_end - pp.tap_begin;
   // bytes one stage receives in total (both CTAs of a pair signal the leader's barrier)
-  const uint32_t a_tx = CTA2 ? 2 * p.a_tx_bytes : p.a_tx_bytes;
-  const uint32_t w_tx = CTA2 ? 2 * p.w_stage_bytes : p.w_stage_bytes;
+  const uint32_t a_tx = CTA2 ? 2 * pp.a_tx_bytes : pp.a_tx_bytes;
+  const uint32_t w_tx = CTA2 ? 2 * pp.w_stage_bytes : pp.w_stage_bytes;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0 && !(p.desc_variant & 16)) {
+    if (lane == 0 && !(pp.desc_variant & 16)) {
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       bool first = true;
-      for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
+      for (int tile = tile0; tile < pp.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
-        for (int c = 0; c < p.cin_chunks; ++c) {
-          if (p.mode != 1) {
+        int nskip = 0;
+        for (int c = 0; c < pp.cin_chunks; ++c) {
+          if (pp.mode != 1) {
             mbar_wait(a_empty(sa), pa ^ 1);
             if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
             if constexpr (CTA2)
-              tma_load_4d_2sm(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk,
+              tma_load_4d_2sm(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), c * kChunk,
                               tc.x0 - 1, tc.y0 - 1, tc.t);
             else
-              tma_load_4d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
+              tma_load_4d(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
                           tc.y0 - 1, tc.t);
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
           }
-          for (int tap = p.tap_begin; tap < p.tap_end; ++tap) {
-            if (p.mode == 1) {
+          for (int tap = pp.tap_begin; tap < pp.tap_end; ++tap) {
+            if (pp.mode == 1) {
               // stride 2: input (2y+dy-1, 2x+dx-1) seen through the [T][H/2][2][W/2][2*C] view
               const int dy = tap / 3, dx = tap - dy * 3;
               const int px = (dx == 1) ? 0 : 1, x2 = tc.x0 + ((dx == 0) ? -1 : 0);
@@ -815,44 +827,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               mbar_wait(a_empty(sa), pa ^ 1);
               if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
               if constexpr (CTA2)
-                tma_load_5d_2sm(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
-                                px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
+                tma_load_5d_2sm(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa),
+                                px * pp.cin_total + c * kChunk, x2, py, y2, tc.t);
               else
-                tma_load_5d(a_base + sa * p.a_stage_bytes, &map_a, a_full(sa),
-                            px * p.cin_total + c * kChunk, x2, py, y2, tc.t);
-              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+                tma_load_5d(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa),
+                            px * pp.cin_total + c * kChunk, x2, py, y2, tc.t);
+              if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
             }
-            if (!p.w_resident || first) {
+            if (!pp.w_resident || first) {
               mbar_wait(w_empty(sw), pw ^ 1);
               if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
-              const size_t blk = static_cast<size_t>(tc.nt * p.cin_chunks + c) * ntaps + (tap - p.tap_begin);
+              const size_t blk = static_cast<size_t>(tc.nt * pp.cin_chunks + c) * ntaps + (tap - pp.tap_begin);
               if constexpr (CTA2) {
                 // each CTA of the pair stages half of the N rows of this (chunk, tap) filter slab
-                tma_load_2d_2sm(w_base + sw * p.w_stage_bytes, &map_w, w_full(sw), 0,
-                                (static_cast<int>(blk) * 2 + static_cast<int>(rank)) * p.w_rows_cta);
+                tma_load_2d_2sm(w_base + sw * pp.w_stage_bytes, &map_w, w_full(sw), 0,
+                                (static_cast<int>(blk) * 2 + static_cast<int>(rank)) * pp.w_rows_cta);
               } else {
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + blk * p.w_stage_bytes;
-                bulk_load(w_base + sw * p.w_stage_bytes, src, p.w_stage_bytes, w_full(sw));
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + blk * pp.w_stage_bytes;
+                bulk_load(w_base + sw * pp.w_stage_bytes, src, pp.w_stage_bytes, w_full(sw));
               }
-              if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
+              if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
             }
-          }
-        }
-        if constexpr (CTA2 && R == 1) {
-          // skip operand of this tile: block bb = GEMM columns [64 bb, +64) = 64 channels of one
-          // sub-pixel; in the [T][2H][W][2][C] view of the skip tensor that is a plain [128 px][64 ch]
-          // box, two of which share one A stage
-          for (int s2 = 0; s2 < p.skip_mma; s2 += 2) {
-            mbar_wait(a_empty(sa), pa ^ 1);
-            if (rank == 0) mbar_expect_tx(a_full(sa), 2u * 2u * 16384u);
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const int n = tc.nt * NTILE + (s2 + b) * 64;
-              const int q = n >> p.out_C_log2, ch = n & (p.out_C - 1);
-              tma_load_4d_2sm(a_base + sa * p.a_stage_bytes + b * 16384u, &map_s, a_full(sa),
-                              (q & 1) * p.out_C + ch, tc.x0, 2 * tc.y0 + (q >> 1), tc.t + p.skip_t0);
+            if constexpr (CTA2 && R == 1 && (MASK & EPI_PIXSHUF) != 0) {
+              // Skip operand (ConvParams::skip_mma): block bb = GEMM columns [64 bb, +64) = 64 channels
+              // of one sub-pixel; in the [T][2H][W][2][C] view of the skip tensor that is a plain
+              // [128 px][64 ch] box, exactly one filter-ring slot.  The blocks ride in the FILTER ring,
+              // one after every fourth slab: its slots turn over every few hundred cycles and it is
+              // five deep, so a stage with almost no MMA work does not let the pipeline run dry
+              // (in the 2-deep activation ring it did).
+              if (nskip < pp.skip_mma && (((c * ntaps + tap - pp.tap_begin) + 1) & 3) == 0) {
+                mbar_wait(w_empty(sw), pw ^ 1);
+                if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
+                const int n = tc.nt * NTILE + nskip * 64;
+                const int q = n >> pp.out_C_log2, ch = n & (pp.out_C - 1);
+                tma_load_4d_2sm(w_base + sw * pp.w_stage_bytes, &map_s, w_full(sw), (q & 1) * pp.out_C + ch,
+                                tc.x0, 2 * tc.y0 + (q >> 1), tc.t + pp.skip_t0);
+                ++nskip;
+                if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
+              }
             }
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
         first = false;
@@ -869,12 +882,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t leader = elect_one();
       constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);  // SW128, version 1, SBO 1024
       const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
-      const bool no_mma = (p.desc_variant & 2) != 0;
-      const bool no_load = (p.desc_variant & 16) != 0;
+      const bool no_mma = (pp.desc_variant & 2) != 0;
+      const bool no_load = (pp.desc_variant & 16) != 0;
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       uint32_t it = 0;
       bool stacked = false;
-      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = (p.mode == 2);
+      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = (pp.mode == 2);
       if (stacked) {
         // ---- 64->64 stages, vertical taps stacked in N -------------------------------------------
         // The two output-row accumulators sit side by side in TMEM (columns [0,64) and [64,128)).
@@ -887,7 +900,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t idesc64 = make_idesc(64, BF16 ? 1 : 0, 256);
         const uint32_t idesc128 = make_idesc(128, BF16 ? 1 : 0, 256);
         const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
-        for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
+        for (int tile = tile0; tile < pp.total_tiles; tile += tstep, ++it) {
           const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
           mbar_wait(acc_empty(buf), acc_phase ^ 1);
           if (!no_load) {
@@ -896,7 +909,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-          const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t a_lo0 = (((a_base + sa * pp.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
           if (leader && !no_mma) {
 #pragma unroll
             for (int hr = 0; hr < 4; ++hr) {
@@ -919,35 +932,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             umma_commit_2sm(acc_full(buf));
           }
           __syncwarp();
-          if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+          if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
         }
       } else
-      for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
+      for (int tile = tile0; tile < pp.total_tiles; tile += tstep, ++it) {
         const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
       const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(acc_empty(buf), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-        for (int c = 0; c < p.cin_chunks; ++c) {
-          if (p.mode == 0 && !no_load) {
+        int nskip = 0;
+        for (int c = 0; c < pp.cin_chunks; ++c) {
+          if (pp.mode == 0 && !no_load) {
             mbar_wait(a_full(sa), pa);
             tc_fence_after();
           }
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if (tap < p.tap_begin || tap >= p.tap_end) continue;
-            if (p.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
-            if ((!p.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
+            if (tap < pp.tap_begin || tap >= pp.tap_end) continue;
+            if (pp.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
+            if ((!pp.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
             tc_fence_after();
             const int dy = tap / 3, dx = tap % 3;
             // start-address words (>>4) of this stage; LBO field = 1 (unused for SW128 K-major)
-            const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t b_lo0 = (((w_base + sw * p.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t first = (c == 0 && tap == p.tap_begin) ? 0u : 1u;
+            const uint32_t a_lo0 = (((a_base + sa * pp.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = (((w_base + sw * pp.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t first = (c == 0 && tap == pp.tap_begin) ? 0u : 1u;
             if (leader && !no_mma) {
 #pragma unroll
               for (int r = 0; r < R; ++r) {
-                const uint32_t a_off = (p.mode == 0 && !(p.desc_variant & 8))
+                const uint32_t a_off = (pp.mode == 0 && !(pp.desc_variant & 8))
                     ? static_cast<uint32_t>(((r + dy) * kHaloPx + dx) * 8)
                     : static_cast<uint32_t>(r * (kRunPx * 8));
 #pragma unroll
@@ -963,43 +977,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             if (leader) {
               if constexpr (CTA2) {
-                if (!p.w_resident) umma_commit_2sm(w_empty(sw));
-                if (p.mode == 1) umma_commit_2sm(a_empty(sa));
+                if (!pp.w_resident) umma_commit_2sm(w_empty(sw));
+                if (pp.mode == 1) umma_commit_2sm(a_empty(sa));
               } else {
-                if (!p.w_resident) umma_commit(w_empty(sw));
-                if (p.mode == 1) umma_commit(a_empty(sa));
+                if (!pp.w_resident) umma_commit(w_empty(sw));
+                if (pp.mode == 1) umma_commit(a_empty(sa));
               }
             }
             __syncwarp();
-            if (++sw == (uint32_t)p.w_stages) { sw = 0; pw ^= 1; }
-            if (p.mode == 1) {
-              if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
+            if (pp.mode == 1) {
+              if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
+            }
+            if constexpr (CTA2 && R == 1 && (MASK & EPI_PIXSHUF) != 0) {
+              // skip block in the filter ring (see the producer): D[:, 64 bb .. +64) += S_bb * I
+              if (nskip < pp.skip_mma && (((c * (pp.tap_end - pp.tap_begin) + tap - pp.tap_begin) + 1) & 3) == 0) {
+                if (!no_load) mbar_wait(w_full(sw), pw);
+                tc_fence_after();
+                const uint32_t s_lo0 = (((w_base + sw * pp.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t id_lo0 = ((id_base & 0x3FFFFu) >> 4) | (1u << 16);
+                if (leader && !no_mma) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(tmem_acc + nskip * 64, desc_hi | (s_lo0 + k * 2u), desc_hi | (id_lo0 + k * 2u),
+                                 make_idesc(64, BF16 ? 1 : 0, 256), 1u);
+                }
+                if (leader) umma_commit_2sm(w_empty(sw));
+                __syncwarp();
+                ++nskip;
+                if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
+              }
             }
           }
-          if (p.mode == 0) {
+          if (pp.mode == 0) {
             if (leader) { if constexpr (CTA2) umma_commit_2sm(a_empty(sa)); else umma_commit(a_empty(sa)); }
             __syncwarp();
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
-          }
-        }
-        if constexpr (CTA2 && R == 1) {
-          const uint32_t idesc_id = make_idesc(64, BF16 ? 1 : 0, 256);
-          const uint32_t id_lo0 = ((id_base & 0x3FFFFu) >> 4) | (1u << 16);
-          for (int s2 = 0; s2 < p.skip_mma; s2 += 2) {
-            if (!no_load) mbar_wait(a_full(sa), pa);
-            tc_fence_after();
-            const uint32_t a_lo0 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            if (leader && !no_mma) {
-#pragma unroll
-              for (int b = 0; b < 2; ++b)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_2sm(tmem_acc + (s2 + b) * 64, desc_hi | (a_lo0 + b * (16384u >> 4) + k * 2u),
-                               desc_hi | (id_lo0 + k * 2u), idesc_id, 1u);
-            }
-            if (leader) umma_commit_2sm(a_empty(sa));
-            __syncwarp();
-            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+            if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
           }
         }
         if (leader) { if constexpr (CTA2) umma_commit_2sm(acc_full(buf)); else umma_commit(acc_full(buf)); }
@@ -1022,7 +1035,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     };
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     // register copy of the epilogue parameters, except in the register-starved general instance
-    const EpiParams e(p);
+    using EP = typename std::conditional<(MASK & EPI_SKIP) != 0, const ConvParams&, const EpiParams>::type;
+    EP e(p);
     EpiLane el = epi_lane<MASK>(e, lane);
     uint32_t it = 0;
     // temp1 residual operand (raw fp32 network input, channels 0..2) of this warp's first unit,
