@@ -312,6 +312,8 @@ static size_t staging_bytes(int ew) { return (size_t)ew * kStageBytesPerWarp; } 
 struct StageLaunch;
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st);
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
+static int launch_pipe(const StageLaunch& L, cudaStream_t st);
 struct StageLaunch {
   CUtensorMap map;      // activations
   CUtensorMap map_w;    // packed weights (CTA-pair kernels)
@@ -329,10 +331,25 @@ struct StageLaunch {
   int first_inc = 4;
 };
 
+// pick the compile-time pipeline shape (conv_tc.cuh PIPE) the plan asks for
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
+  if constexpr (CTA2) {
+    const int mode = L.p.mode, res = L.p.w_resident;
+    if constexpr (NTILE == 64 && R == 2) {
+      if (mode == 2 && res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 2>(L, st);
+    } else {
+      if (mode == 0 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 0>(L, st);
+      if constexpr ((MASK & (EPI_PIXSHUF | EPI_RESID_IN)) == 0)
+        if (mode == 1 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 1>(L, st);
+    }
+  }
+  return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 3>(L, st);
+}
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
+static int launch_pipe(const StageLaunch& L, cudaStream_t st) {
   static bool attr_done[64] = {};      // per device: the attribute is per (function, device)
-  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK, EW>;
+  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK, EW, PIPE>;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {

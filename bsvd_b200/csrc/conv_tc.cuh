@@ -681,7 +681,10 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 // --------------------------------------------------------------------------------------------
 // The kernel
 // --------------------------------------------------------------------------------------------
-template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
+// PIPE: compile-time pipeline shape, so the producer / MMA loops carry no per-tap parameter tests:
+//   0 halo tile + streamed filter slabs   1 stride-2 per-tap boxes + streamed slabs
+//   2 stacked 64->64 (resident bank)      3 generic: mode / w_resident read from ConvParams
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o,
@@ -766,7 +769,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   if constexpr (NTILE == 64 && R == 2 && CTA2) {
-    if (p.mode == 2) {
+    if ((PIPE == 3 ? p.mode : PIPE) == 2) {
       // stacked mode accumulates from the first MMA on: start from zeroed accumulators
       if (warp >= 2) {
         const uint32_t lb = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -790,7 +793,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int a_stages, w_stages, cin_chunks, tap_begin, tap_end, mode, w_resident, total_tiles, desc_variant,
         skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0;
     uint32_t a_stage_bytes, w_stage_bytes, a_tx_bytes;
-  } const pp = {p.a_stages, p.w_stages, p.cin_chunks, p.tap_begin, p.tap_end, p.mode, p.w_resident,
+  } const pp = {p.a_stages, p.w_stages, p.cin_chunks, p.tap_begin, p.tap_end,
+                PIPE == 3 ? p.mode : PIPE, PIPE == 3 ? p.w_resident : (PIPE == 2 ? 1 : 0),
                 p.total_tiles, p.desc_variant, p.skip_mma, p.w_rows_cta, p.cin_total, p.out_C_log2, p.out_C,
                 p.skip_t0, p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
   const int ntaps = pp.tap_end - pp.tap_begin;
@@ -1087,7 +1091,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
       // accumulator drained: the (leader's) MMA warp may reuse the buffer
       bool stacked = false;
-      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = (p.mode == 2);
+      if constexpr (NTILE == 64 && R == 2 && CTA2) stacked = ((PIPE == 3 ? p.mode : PIPE) == 2);
       auto release_acc = [&]() {
         if (stacked) tmem_st_wait();           // the zeros written behind the loads have landed
         tc_fence_before();
