@@ -336,7 +336,9 @@ template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   if constexpr (CTA2) {
     const int mode = L.p.mode, res = L.p.w_resident;
-    if constexpr (NTILE == 64 && R == 2) {
+    if (L.p.desc_variant != 0 || L.p.tap_begin != 0 || L.p.tap_end != (mode == 2 ? 3 : 9)) {
+      // debug switches / partial tap ranges only exist in the generic pipeline
+    } else if constexpr (NTILE == 64 && R == 2) {
       if (mode == 2 && res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 2>(L, st);
     } else {
       if (mode == 0 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 0>(L, st);

@@ -793,7 +793,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int a_stages, w_stages, cin_chunks, tap_begin, tap_end, mode, w_resident, total_tiles, desc_variant,
         skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0;
     uint32_t a_stage_bytes, w_stage_bytes, a_tx_bytes;
-  } const pp = {p.a_stages, p.w_stages, p.cin_chunks, p.tap_begin, p.tap_end,
+  } const pp = {p.a_stages, p.w_stages, p.cin_chunks, PIPE == 3 ? p.tap_begin : 0,
+                PIPE == 3 ? p.tap_end : (PIPE == 2 ? 3 : 9),
                 PIPE == 3 ? p.mode : PIPE, PIPE == 3 ? p.w_resident : (PIPE == 2 ? 1 : 0),
                 p.total_tiles, p.desc_variant, p.skip_mma, p.w_rows_cta, p.cin_total, p.out_C_log2, p.out_C,
                 p.skip_t0, p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
@@ -938,34 +939,44 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           __syncwarp();
           if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
         }
-      } else
+      } else {
+      // With a compile-time pipeline shape (PIPE != 3) the loop carries no debug switches and the
+      // tap range is 0..9: everything per tap is one barrier wait, the MMAs, one commit.
+      constexpr bool kGen = (PIPE == 3);
+      const int tap_b = kGen ? pp.tap_begin : 0, tap_e = kGen ? pp.tap_end : 9;
+      const bool dbg_no_load = kGen && no_load, dbg_no_mma = kGen && no_mma;
+      const bool dbg_flat_a = kGen && (pp.desc_variant & 8);
+      const uint32_t a_lo_base = ((a_base & 0x3FFFFu) >> 4) | (1u << 16), a_lo_step = pp.a_stage_bytes >> 4;
+      const uint32_t w_lo_base = ((w_base & 0x3FFFFu) >> 4) | (1u << 16), w_lo_step = pp.w_stage_bytes >> 4;
       for (int tile = tile0; tile < pp.total_tiles; tile += tstep, ++it) {
         const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
-      const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
+        const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(acc_empty(buf), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kAccCols;
         int nskip = 0;
         for (int c = 0; c < pp.cin_chunks; ++c) {
-          if (pp.mode == 0 && !no_load) {
+          if (pp.mode == 0 && !dbg_no_load) {
             mbar_wait(a_full(sa), pa);
             tc_fence_after();
           }
+          uint32_t a_lo0 = a_lo_base + sa * a_lo_step;     // mode 1: recomputed per tap below
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if (tap < pp.tap_begin || tap >= pp.tap_end) continue;
-            if (pp.mode == 1 && !no_load) mbar_wait(a_full(sa), pa);
-            if ((!pp.w_resident || it == 0) && !no_load) mbar_wait(w_full(sw), pw);
+            if (kGen && (tap < tap_b || tap >= tap_e)) continue;
+            if (pp.mode == 1) {
+              if (!dbg_no_load) mbar_wait(a_full(sa), pa);
+              a_lo0 = a_lo_base + sa * a_lo_step;
+            }
+            if ((!pp.w_resident || it == 0) && !dbg_no_load) mbar_wait(w_full(sw), pw);
             tc_fence_after();
             const int dy = tap / 3, dx = tap % 3;
-            // start-address words (>>4) of this stage; LBO field = 1 (unused for SW128 K-major)
-            const uint32_t a_lo0 = (((a_base + sa * pp.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t b_lo0 = (((w_base + sw * pp.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t first = (c == 0 && tap == pp.tap_begin) ? 0u : 1u;
-            if (leader && !no_mma) {
+            const uint32_t b_lo0 = w_lo_base + sw * w_lo_step;
+            const uint32_t first = (c == 0 && tap == tap_b) ? 0u : 1u;
+            if (leader && !dbg_no_mma) {
 #pragma unroll
               for (int r = 0; r < R; ++r) {
-                const uint32_t a_off = (pp.mode == 0 && !(pp.desc_variant & 8))
+                const uint32_t a_off = (pp.mode == 0 && !dbg_flat_a)
                     ? static_cast<uint32_t>(((r + dy) * kHaloPx + dx) * 8)
                     : static_cast<uint32_t>(r * (kRunPx * 8));
 #pragma unroll
@@ -995,12 +1006,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             if constexpr (CTA2 && R == 1 && (MASK & EPI_PIXSHUF) != 0) {
               // skip block in the filter ring (see the producer): D[:, 64 bb .. +64) += S_bb * I
-              if (nskip < pp.skip_mma && (((c * (pp.tap_end - pp.tap_begin) + tap - pp.tap_begin) + 1) & 3) == 0) {
-                if (!no_load) mbar_wait(w_full(sw), pw);
+              if (nskip < pp.skip_mma && (((c * (tap_e - tap_b) + tap - tap_b) + 1) & 3) == 0) {
+                if (!dbg_no_load) mbar_wait(w_full(sw), pw);
                 tc_fence_after();
-                const uint32_t s_lo0 = (((w_base + sw * pp.w_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t s_lo0 = w_lo_base + sw * w_lo_step;
                 const uint32_t id_lo0 = ((id_base & 0x3FFFFu) >> 4) | (1u << 16);
-                if (leader && !no_mma) {
+                if (leader && !dbg_no_mma) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_f16_2sm(tmem_acc + nskip * 64, desc_hi | (s_lo0 + k * 2u), desc_hi | (id_lo0 + k * 2u),
@@ -1021,6 +1032,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         if (leader) { if constexpr (CTA2) umma_commit_2sm(acc_full(buf)); else umma_commit(acc_full(buf)); }
         __syncwarp();
+      }
       }
     }
   } else {
