@@ -394,6 +394,10 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
   if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
   const int f = L.p.flags & kMaskAll;
   {
+    if (L.p.tma_out) {     // no temporal shift on the output: units leave through TMA stores
+      if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain | EPI_TMA_OUT, 8>(L, st);
+      if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid | EPI_TMA_OUT, 8>(L, st);
+    }
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
     if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
     if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
@@ -456,8 +460,12 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
                         !s.first_im2col && !s.final_out && (!s.shift || up_shift_on);
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
-  const bool tma_out = tma_on && skip_mma && !s.shift && !s.relu6;
-  const size_t kStagingBytes = staging_bytes(L->ew) * (tma_out ? 2 : 1) + (skip_mma ? 4096 : 0);
+  const bool tma_out = tma_on && cta2 && !s.shift && !(s.skip && !skip_mma) && !s.first_im2col &&
+                       !s.final_out && !(desc_variant & ~(2 | 4 | 16 | 128));
+  // two staging tiles per warp when they fit; the stacked 64->64 stages (resident 72 KB bank) have
+  // room for one, whose TMA read is awaited right before it is rewritten
+  const int stg_bufs = (tma_out && !s.stacked) ? 2 : 1;
+  const size_t kStagingBytes = staging_bytes(L->ew) * stg_bufs + (skip_mma ? 4096 : 0);
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;
@@ -564,7 +572,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.skip = io.skip; p.skip_C = io.skip_C; p.skip_frame_stride = io.skip_frame_stride;
   p.resid_in = io.resid_in; p.resid_C = io.resid_C; p.aux_out = io.aux_out;
   p.fold = p.out_C / 8;
-  p.stg_bytes_per_warp = kStageBytesPerWarp * (tma_out ? 2 : 1);
+  p.stg_bytes_per_warp = kStageBytesPerWarp * stg_bufs;
   p.skip_mma = skip_mma ? s.ntile / 64 : 0;
   p.tma_out = tma_out ? 1 : 0;
   if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");

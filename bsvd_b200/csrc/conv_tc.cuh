@@ -431,6 +431,7 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
   int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0;
+  uint32_t stg_bytes_per_warp;
   void* out; void* out_prev; void* out_next; void* aux_out;
   const void* skip; const float* resid_in;
   long long out_frame_stride, skip_frame_stride;
@@ -438,7 +439,7 @@ struct EpiParams {
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
-        out_t0(p.out_t0),
+        out_t0(p.out_t0), stg_bytes_per_warp(p.stg_bytes_per_warp),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
@@ -510,11 +511,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
                                               int lane, const float (&rin)[3], bool use_rin,
                                               const CUtensorMap* map_o = nullptr) {
   const int flags = p.flags & MASK;
-  if constexpr ((MASK & EPI_TMA_OUT) != 0) {
-    // the TMA store that last read this staging buffer (two units ago) must have drained it
-    if (lane == 0) bulk_wait_group_read<1>();
-    __syncwarp();
-  }
+
   // ------------------------------ phase 0 ------------------------------
   // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
   if constexpr ((MASK & EPI_SKIP) != 0) {
@@ -590,6 +587,15 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
         o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
         o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
       }
+    }
+    if constexpr ((MASK & EPI_TMA_OUT) != 0) {
+      // the TMA store that last read this staging tile (the previous unit's, or with two tiles per
+      // warp the one before) must have drained it; awaited as late as possible
+      if (lane == 0) {
+        if (p.stg_bytes_per_warp > kStageBytesPerWarp) bulk_wait_group_read<1>();
+        else bulk_wait_group_read<0>();
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -1046,7 +1052,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t stg0 = stg_base + ew * p.stg_bytes_per_warp;
     uint32_t ucount = 0;                       // TMA stores: units alternate between two staging tiles
     auto next_stg = [&]() -> uint32_t {
-      if constexpr ((MASK & EPI_TMA_OUT) != 0) return stg0 + (ucount++ & 1u) * kStageBytesPerWarp;
+      if constexpr ((MASK & EPI_TMA_OUT) != 0)
+        return stg0 + ((p.stg_bytes_per_warp > kStageBytesPerWarp) ? (ucount++ & 1u) * kStageBytesPerWarp : 0u);
       else return stg0;
     };
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
