@@ -397,6 +397,8 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
     if (L.p.tma_out) {     // no temporal shift on the output: units leave through TMA stores
       if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain | EPI_TMA_OUT, 8>(L, st);
       if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid | EPI_TMA_OUT, 8>(L, st);
+      if constexpr (NTILE != 64)
+        if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift | EPI_TMA_OUT, 8>(L, st);
     }
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
     if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
@@ -460,7 +462,9 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
                         !s.first_im2col && !s.final_out && (!s.shift || up_shift_on);
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
-  const bool tma_out = tma_on && cta2 && !s.shift && !(s.skip && !skip_mma) && !s.first_im2col &&
+  static const int tma_shift_on = [] { const char* e = getenv("BSVD_B200_TMA_SHIFT"); return e ? atoi(e) : 0; }();   // measured: -3 % when on
+  const bool tma_out = tma_on && cta2 && (!s.shift || (tma_shift_on && !s.pixshuf)) &&
+                       !(s.skip && !skip_mma) && !s.first_im2col &&
                        !s.final_out && !(desc_variant & ~(2 | 4 | 16 | 128));
   // two staging tiles per warp when they fit; the stacked 64->64 stages (resident 72 KB bank) have
   // room for one, whose TMA read is awaited right before it is rewritten

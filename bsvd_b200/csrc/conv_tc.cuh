@@ -606,6 +606,15 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
     // ------------------------------ phase 2 (TMA) ------------------------------
     // The staging tile [32 px][64 B] with its XOR pattern IS the SWIZZLE_64B box layout: one
     // cp.async.bulk.tensor store moves the unit; the tensor map clips pixels beyond the image.
+    // With a temporal shift only the unit(s) holding the two folds take the routed LSU path below.
+    bool routed = false;
+    if constexpr ((MASK & EPI_SHIFT) != 0) {
+      const int cb = (p.flags & EPI_PIXSHUF) ? (nbase & (p.out_C - 1)) : nbase;
+      routed = (flags & EPI_SHIFT) && cb < 2 * p.fold;
+    }
+    if (routed) {
+      if (lane == 0) bulk_commit_group();     // empty group: keeps the per-unit group count exact
+    } else {
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -621,6 +630,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       bulk_commit_group();      // one group per unit, empty or not: keeps the wait_group count exact
     }
     return;
+    }
   }
   __syncwarp();
   // ------------------------------ phase 2 ------------------------------
