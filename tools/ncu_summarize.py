@@ -23,8 +23,9 @@ lines = ["| # | kernel | time us | DRAM rd MB | DRAM wr MB | DRAM GB/s | tensor 
 agg = OrderedDict()
 for i, r in enumerate(data):
     name = r[col["Kernel Name"]]
-    m = re.search(r"conv3x3_tc_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d+)(?:, (?:\(int\))?\d+)?>", name)
-    short = f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}> cta2={m.group(4)} mask={m.group(5)}" if m else name.split("(")[0][-40:]
+    m = re.search(r"conv3x3_tc_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d+)(?:, (?:\(int\))?(\d+))?(?:, (?:\(int\))?(\d+))?>", name)
+    short = (f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}> cta2={m.group(4)} mask={m.group(5)} pipe={m.group(7)}"
+             if m else name.split("(")[0][-40:])
     key = f"conv3x3_tc_kernel<{m.group(1)},{m.group(2)}>" if m else ("first_conv_kernel" if "first_conv" in name else "final_conv_kernel" if "final_conv" in name else short)
     t = to_us(g(r, "gpu__time_duration.sum"), unit("gpu__time_duration.sum"))
     rd = to_bytes(g(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum"))
