@@ -249,6 +249,24 @@ class BSVD(nn.Module):
         with torch.no_grad():
             return self._run_stream(input_seq)
 
+    def denoise_sequence(self, noisy, sigma):
+        """noisy [F,3,H,W] in [0,1] (any H, W), sigma = noise std in [0,1] (None for a blind model)
+        -> denoised [F,3,H,W] clamped to [0,1]: temp_denoise + DenoisingModel.padding_input /
+        crop_output (validation_seq_infer.py:10-31, denoising_model.py:133-168) in one C-ABI call;
+        reflect padding, the constant noise map, the clamp and the crop happen inside the first and
+        last kernels (bsvd_denoise_clip)."""
+        dev = noisy.device if noisy.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            lib = self._ensure_handle(dev)
+            x = noisy.detach().to(dev).float().contiguous()
+            Fr, Cc, H, W = x.shape
+            assert Cc == 3, "denoise_sequence takes RGB frames"
+            out = torch.empty((Fr, 3, H, W), dtype=torch.float32, device=dev)
+            capi.check(lib.bsvd_denoise_clip(
+                self._handle, x.data_ptr(), -1.0 if sigma is None else float(sigma), out.data_ptr(),
+                Fr, H, W, torch.cuda.current_stream(dev).cuda_stream))
+        return out
+
     def denoise_host(self, input_host, noise_map_host=None, out_host=None):
         """End-to-end entry with HOST buffers (pinned recommended): H2D + forward + D2H inside the
         C ABI (bsvd_forward_clip_host).  input_host: fp32 [T,C,H,W] CPU tensor -> fp32 [T,3,H,W]."""

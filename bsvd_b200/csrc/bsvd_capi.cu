@@ -725,6 +725,9 @@ struct bsvd_handle {
   uint16_t* bufS = nullptr;   // compact [T][H][W][4] copy of temp1's output channels 0..3 (skip1 of temp2)
   std::vector<StageLaunch> plan;
   int last_launches = 0;
+  // raw-image view for the fused caller entry (0 / off for plain bsvd_forward_clip)
+  int src_H = 0, src_W = 0, use_sigma = 0, clamp01 = 0;
+  float sigma_const = 0.f;
   // per-stage event timing
   int profiling = 0;
   std::vector<std::vector<cudaEvent_t>> ev_sets;   // each: BSVD_NUM_STAGES + 1 events
@@ -992,7 +995,7 @@ size_t bsvd_workspace_bytes(const bsvd_handle* h) { return h ? h->ws_bytes : 0; 
 int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
                       int in_c, int H, int W, void* stream) {
   if (!h || !in || !out) return fail("null argument");
-  if (check_hw(T, in_c, H, W, noise_map != nullptr, h->cfg.in_ch)) return 1;
+  if (check_hw(T, in_c, H, W, noise_map != nullptr || h->use_sigma, h->cfg.in_ch)) return 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
   if (build_clip_plan(h, in, noise_map, out, T, in_c, H, W)) return 1;
@@ -1014,12 +1017,88 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   h->plan[15].p.resid_in = in;          // temp1 residual reads the raw input (skip1)
   h->plan[15].p.resid_C = in_c;
   h->plan[BSVD_NUM_LAYERS - 1].p.out = out;
+  // raw-image view of the first / residual / last kernels (bsvd_denoise_clip sets h->src_*)
+  for (int l : {0, 15, BSVD_NUM_LAYERS - 1}) {
+    ConvParams& q = h->plan[l].p;
+    q.src_H = h->src_H; q.src_W = h->src_W;
+    q.use_sigma = h->use_sigma; q.sigma_const = h->sigma_const; q.clamp01 = h->clamp01;
+  }
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
     if (launch_stage(h->plan[l], st)) return 1;
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[l + 2], st));
     ++launches;
   }
   h->last_launches = launches;
+  return 0;
+}
+
+int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
+                      void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  if (H < 2 || W < 2) return fail("reflect padding needs H, W >= 2 (got %dx%d)", H, W);
+  const bool blind = h->cfg.in_ch == 3;
+  if (blind != (sigma < 0.f))
+    return fail(blind ? "blind model: pass sigma < 0" : "non-blind model needs sigma >= 0");
+  const int Hp = (H + 3) / 4 * 4, Wp = (W + 3) / 4 * 4;
+  if (Hp - H >= H || Wp - W >= W) return fail("image too small to reflect-pad to a multiple of 4");
+  h->src_H = H; h->src_W = W; h->use_sigma = blind ? 0 : 1; h->sigma_const = sigma; h->clamp01 = 1;
+  // a 3-channel raw input: the 4th (noise-map) slot is synthesised by the first kernel
+  const int rc = bsvd_forward_clip(h, in, nullptr, out, T, 3, Hp, Wp, stream);
+  h->src_H = h->src_W = 0; h->use_sigma = 0; h->clamp01 = 0;
+  return rc;
+}
+
+// ---- PSNR per frame (calculate_psnr_float, BasicSR/basicsr/metrics/psnr_ssim.py:130-168) -----------
+constexpr int kPsnrBlocks = 64;
+static __global__ void psnr_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int C,
+                                           int H, int W, int cb, double* __restrict__ part) {
+  const int t = blockIdx.y;
+  const int hh = H - 2 * cb, ww = W - 2 * cb;
+  const long long n = static_cast<long long>(C) * hh * ww;
+  const long long base = static_cast<long long>(t) * C * H * W;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % ww);
+    const long long r = i / ww;
+    const int y = static_cast<int>(r % hh), c = static_cast<int>(r / hh);
+    const long long o = base + (static_cast<long long>(c) * H + (y + cb)) * W + (x + cb);
+    const float d = a[o] - b[o];
+    acc += static_cast<double>(d) * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) part[t * gridDim.x + blockIdx.x] = acc;
+  }
+}
+static __global__ void psnr_final_kernel(const double* __restrict__ part, int nb, double n, float* psnr) {
+  const int t = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 32) acc += part[t * nb + i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) {
+    const double mse = acc / n;
+    psnr[t] = mse == 0.0 ? __int_as_float(0x7f800000) : static_cast<float>(-10.0 * log10(mse));
+  }
+}
+int bsvd_psnr(const float* a, const float* b, int T, int C, int H, int W, int crop_border, float* psnr,
+              void* stream) {
+  if (!a || !b || !psnr) return fail("null argument");
+  if (T < 1 || C < 1 || crop_border < 0 || H - 2 * crop_border < 1 || W - 2 * crop_border < 1)
+    return fail("bad PSNR shape T=%d C=%d %dx%d crop_border=%d", T, C, H, W, crop_border);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* part = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(double) * T * kPsnrBlocks, st));
+  psnr_partial_kernel<<<dim3(kPsnrBlocks, T), 256, 0, st>>>(a, b, C, H, W, crop_border, part);
+  const double n = static_cast<double>(C) * (H - 2 * crop_border) * (W - 2 * crop_border);
+  psnr_final_kernel<<<T, 32, 0, st>>>(part, kPsnrBlocks, n, psnr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(part, st));
   return 0;
 }
 

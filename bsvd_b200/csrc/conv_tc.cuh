@@ -107,7 +107,17 @@ struct ConvParams {
   int tma_out;          // 1: the epilogue stores its units with TMA (EPI_TMA_OUT instances)
   int skip_t0, out_t0;  // frame coordinate offsets into map_s / map_o (streaming: ring slot)
   uint32_t stg_bytes_per_warp;   // epilogue staging per warp: 2 KB, or 4 KB (double-buffered) with TMA stores
+  // ---- callers either side of the path folded into the first / last kernels (bsvd_denoise_clip) ----
+  // The network runs on H x W (multiples of 4); the raw input / final output are src_H x src_W images
+  // (0 = same): reads beyond them are reflected (DenoisingModel.padding_input, F.pad 'reflect'),
+  // the final store crops back and optionally clamps to [0,1] (temp_denoise).
+  int src_H, src_W;
+  int use_sigma;        // 1: the 4th input channel is the constant sigma_const (no noise-map tensor)
+  float sigma_const;
+  int clamp01;
 };
+// reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
+__device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }
 
 // --------------------------------------------------------------------------------------------
 // PTX helpers
@@ -432,6 +442,7 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 struct EpiParams {
   int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0;
   uint32_t stg_bytes_per_warp;
+  int src_H, src_W;
   void* out; void* out_prev; void* out_next; void* aux_out;
   const void* skip; const float* resid_in;
   long long out_frame_stride, skip_frame_stride;
@@ -440,6 +451,7 @@ struct EpiParams {
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
         out_t0(p.out_t0), stg_bytes_per_warp(p.stg_bytes_per_warp),
+        src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : p.W),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
@@ -567,9 +579,10 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 #pragma unroll
             for (int i = 0; i < 3; ++i) f[i] = rin[i] - f[i];
           } else {
-            const long long plane = static_cast<long long>(p.H) * p.W;
+            const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : p.W;
+            const long long plane = static_cast<long long>(sH) * sW;
             const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
-                             static_cast<long long>(y) * p.W + x;
+                             static_cast<long long>(reflect_src(y, sH)) * sW + reflect_src(x, sW);
 #pragma unroll
             for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
           }
@@ -1083,9 +1096,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const TileCoord tn = decode_tile<R>(p, tile_idx, CTA2, rank);
           const int y = tn.y0 + u0 / G, x = tn.x0 + quad * 32 + lane;
           if (tn.nt * NTILE + (u0 % G) * 32 == 0 && tn.t < e.T && y < e.H && x < e.W) {
-            const long long plane = static_cast<long long>(e.H) * e.W;
+            const long long plane = static_cast<long long>(e.src_H) * e.src_W;
             const float* r = e.resid_in + (static_cast<long long>(tn.t) * e.resid_C) * plane +
-                             static_cast<long long>(y) * e.W + x;
+                             static_cast<long long>(reflect_src(y, e.src_H)) * e.src_W + reflect_src(x, e.src_W);
 #pragma unroll
             for (int i = 0; i < 3; ++i) rin_next[i] = __ldg(r + i * plane);
           }

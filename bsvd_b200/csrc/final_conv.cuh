@@ -123,7 +123,8 @@ final_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int quad = warp & 3;
     const int half = ew >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const long long plane = static_cast<long long>(p.H) * p.W;
+    const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : p.W;   // crop back to the raw image
+    const long long plane = static_cast<long long>(sH) * sW;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile<kFinalR>(p, tile);
@@ -160,12 +161,16 @@ final_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const float2 s01 = unpack2<BF16>(sk[i].x), s23 = unpack2<BF16>(sk[i].y);
           const float sv[3] = {s01.x, s01.y, s23.x};
           float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane +
-                     static_cast<long long>(y) * p.W + x;
+                     static_cast<long long>(y) * sW + x;
+          if (y < sH && x < sW) {
 #pragma unroll
-          for (int co = 0; co < 3; ++co) {
-            const float conv = __uint_as_float(d[i][0][co]) + __uint_as_float(d[i][1][co]) +
-                               __uint_as_float(d[i][2][co]) + bias_s[co];
-            o[co * plane] = sv[co] - conv;
+            for (int co = 0; co < 3; ++co) {
+              const float conv = __uint_as_float(d[i][0][co]) + __uint_as_float(d[i][1][co]) +
+                                 __uint_as_float(d[i][2][co]) + bias_s[co];
+              float r = sv[co] - conv;
+              if (p.clamp01) r = fminf(fmaxf(r, 0.f), 1.f);      // temp_denoise: torch.clamp(out, 0, 1)
+              o[co * plane] = r;
+            }
           }
         }
       }

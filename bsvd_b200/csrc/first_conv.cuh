@@ -81,7 +81,8 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     // the global-load latency of one group's tile overlaps the stores of the other's.
     const int i = threadIdx.x & 127;             // 0..127
     const int grp = threadIdx.x >> 7;            // 0 / 1
-    const long long plane = static_cast<long long>(p.H) * p.W;
+    const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : p.W;   // raw image (reflected beyond)
+    const long long plane = static_cast<long long>(sH) * sW;
     uint32_t it = grp;
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const uint32_t sa = it % kFirstStages, pa = (it / kFirstStages) & 1;
@@ -96,13 +97,14 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         for (int dx = 0; dx < 3; ++dx) {
           const int xx = x - 1 + dx;
           const bool ok = (yy >= 0) && (yy < p.H) && (xx >= 0) && (xx < p.W);
-          const long long o = static_cast<long long>(yy) * p.W + xx;
+          const long long o = static_cast<long long>(reflect_src(yy, sH)) * sW + reflect_src(xx, sW);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float f = 0.f;
             if (ok) {
               if (c < in_c) f = __ldg(in + (static_cast<long long>(tc.t) * in_c + c) * plane + o);
               else if (nmap) f = __ldg(nmap + static_cast<long long>(tc.t) * plane + o);
+              else if (p.use_sigma) f = p.sigma_const;
             }
             v[rr][dx][c] = f;
           }

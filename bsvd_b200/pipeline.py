@@ -5,8 +5,11 @@
 * temp_denoise (Experimental_root/models/validation_seq_infer.py:10-31): constant sigma map, forward,
   clamp to [0,1].
 
-Pad / clamp / crop run as ordinary torch ops on the device (two cheap full-resolution passes over
-3-channel tensors); the concat with the noise map is folded into the first kernel by the C ABI.
+`denoise_sequence` goes through ONE C-ABI call (bsvd_denoise_clip): reflect padding and the constant
+noise map are synthesised by the first kernel's loads, clamp and crop by the last kernel's stores.
+`denoise_sequence_unfused` keeps the same steps as separate torch ops (the reference's structure);
+the tests check the two against each other.  `psnr_per_frame` is calculate_psnr_float
+(BasicSR/basicsr/metrics/psnr_ssim.py:130-168) on the device.
 """
 from __future__ import annotations
 
@@ -24,7 +27,36 @@ def pad_to_multiple_of_4(seq: torch.Tensor):
     return seq, (ph, pw)
 
 
+def _sigma_scalar(sigma):
+    if torch.is_tensor(sigma):
+        s = float(sigma.flatten()[0])
+        assert abs(float(sigma.float().mean()) - s) < 1e-5     # validation_seq_infer.py:19
+        return s
+    return float(sigma)
+
+
 def denoise_sequence(net, noisy: torch.Tensor, sigma: float | torch.Tensor) -> torch.Tensor:
+    """noisy: [F,3,H,W] in [0,1]; sigma: noise std in [0,1] (scalar or constant map).  Denoised
+    [F,3,H,W] clamped to [0,1] — what DenoisingModel.test produces for one validation folder
+    (pad -> denoise_seq/temp_denoise -> crop), fused into the first/last kernels."""
+    return net.denoise_sequence(noisy, _sigma_scalar(sigma))
+
+
+def psnr_per_frame(a: torch.Tensor, b: torch.Tensor, crop_border: int = 0) -> torch.Tensor:
+    """[F,C,H,W] x2 -> [F] PSNR in dB on the device (bsvd_psnr)."""
+    from . import capi
+    assert a.shape == b.shape and a.is_cuda and b.is_cuda
+    a = a.float().contiguous(); b = b.float().contiguous()
+    Fr, C, H, W = a.shape
+    out = torch.empty(Fr, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        capi.check(capi.load_library().bsvd_psnr(
+            a.data_ptr(), b.data_ptr(), Fr, C, H, W, crop_border, out.data_ptr(),
+            torch.cuda.current_stream(a.device).cuda_stream))
+    return out
+
+
+def denoise_sequence_unfused(net, noisy: torch.Tensor, sigma: float | torch.Tensor) -> torch.Tensor:
     """noisy: [F,3,H,W] in [0,1]; sigma: noise std in [0,1] (scalar or [F,1,H,W] constant map).
     Returns the denoised [F,3,H,W] clamped to [0,1] — what DenoisingModel.test produces for one
     validation folder (pad -> denoise_seq/temp_denoise -> crop)."""

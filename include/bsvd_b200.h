@@ -82,6 +82,26 @@ int bsvd_layer_shape(const bsvd_handle* h, int layer, int* out_ch, int* in_ch, i
 int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out,
                       int T, int in_c, int H, int W, void* stream);
 
+/* -- the callers either side of the path, fused -----------------------------------
+ * replaces temp_denoise (Experimental_root/models/validation_seq_infer.py:10-31) together with
+ * DenoisingModel.padding_input / crop_output (Experimental_root/models/denoising_model.py:133-168):
+ *   in:    device fp32 [T, 3, H, W] noisy frames in [0,1], ANY H, W >= 2
+ *   sigma: noise standard deviation in [0,1]; the constant noise-map channel the reference builds
+ *          with torch.ones(...) * sigma is synthesised inside the first kernel (pass < 0 for a
+ *          blind model)
+ *   out:   device fp32 [T, 3, H, W], clamped to [0,1]
+ * H and W are reflect-padded (bottom/right) to multiples of 4 inside the first kernel's loads and
+ * cropped by the last kernel's stores: no padded copy, no concat, no clamp pass, no crop copy. */
+int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
+                      void* stream);
+
+/* -- on-device PSNR ----------------------------------------------------------------
+ * replaces calculate_psnr_float (BasicSR/basicsr/metrics/psnr_ssim.py:130-168) applied per frame:
+ * a, b: device fp32 [T, C, H, W] in [0,1]; crop_border pixels are ignored on every edge;
+ * psnr: device fp32 [T] <- -10 log10(mean((a-b)^2)) (+inf when identical).  Enqueued on `stream`. */
+int bsvd_psnr(const float* a, const float* b, int T, int C, int H, int W, int crop_border,
+              float* psnr, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, then waits for
  * completion.  This is the end-to-end entry the bench's `e2e` number goes through. */
 int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* noise_map_host,

@@ -288,6 +288,49 @@ def test_denoise_sequence_pad_clamp_crop_like_the_reference_callers():
     assert float(got.min()) >= 0.0 and float(got.max()) <= 1.0
 
 
+@pytest.mark.parametrize("hw", [(30, 45), (33, 50), (32, 48), (31, 130)])
+def test_fused_denoise_entry_is_bit_identical_to_the_unfused_steps(hw):
+    """bsvd_denoise_clip (reflect pad + constant sigma map + clamp + crop inside the first / last
+    kernels) == the same steps as separate torch ops around bsvd_forward_clip, bit for bit."""
+    from bsvd_b200 import pipeline
+    net, _ = make_net()
+    H, W = hw
+    x, _ = O.make_synthetic_clip(3, H, W, seed=51)
+    noisy, sigma = x[:, :3].clamp(0, 1).cuda(), float(x[0, 3, 0, 0])
+    a = pipeline.denoise_sequence(net, noisy, sigma)
+    b = pipeline.denoise_sequence_unfused(net, noisy, sigma)
+    assert a.shape == b.shape == (3, 3, H, W)
+    assert torch.equal(a, b.float())
+    # and the plain forward on the same handle is unaffected afterwards (no state left behind)
+    x4 = O.make_synthetic_clip(2, 32, 48, seed=52)[0].cuda()
+    y1 = net(x4[None])[0]
+    pipeline.denoise_sequence(net, noisy, sigma)
+    assert torch.equal(net(x4[None])[0], y1)
+
+
+def test_psnr_on_device_matches_calculate_psnr_float():
+    """bsvd_psnr == calculate_psnr_float (psnr_ssim.py:130-168) per frame: CHW float [0,1],
+    crop_border, -10 log10(mse), inf when identical."""
+    import numpy as np
+    from bsvd_b200 import pipeline
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(4, 3, 37, 53, generator=g)
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    b[2] = a[2]
+    for cb in (0, 2):
+        got = pipeline.psnr_per_frame(a.cuda(), b.cuda(), cb).cpu()
+        for t in range(4):
+            i, j = a[t].numpy(), b[t].numpy()
+            if cb:
+                i, j = i[:, cb:-cb, cb:-cb], j[:, cb:-cb, cb:-cb]
+            mse = np.mean((i - j) ** 2)
+            ref = float("inf") if mse == 0 else -10 * np.log10(mse)
+            if mse == 0:
+                assert got[t] == float("inf")
+            else:
+                assert abs(float(got[t]) - ref) < 1e-3
+
+
 def test_blind_variant_three_channel_input():
     """blind=True (README.md:66-72 blind checkpoint; InputCvBlock drops the noise map,
     bsvd_arch.py:204-205): 3-channel frames, no noise map; clip and stream schedules vs the oracle."""
