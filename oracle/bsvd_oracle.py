@@ -62,12 +62,20 @@ _BSVD_LAYER_KEYS = (
 SHIFT_LAYERS = (3, 4, 6, 7, 8, 9, 11, 12)
 
 
-def layer_shapes(block: int, in_ch: int = IN_CH):
+# the other configuration the reference trains (options/train/0402_*_blind_c32.yml:63-68: chns
+# [32,64,128], mid_ch 32, blind; interm_ch and act keep their defaults 30 / 'relu',
+# wnet_models.py:51,135,234)
+C32 = dict(chns=(32, 64, 128), mid_ch=32, interm_ch=30, in_ch=3, act="relu")
+
+
+def layer_shapes(block: int, in_ch: int = IN_CH, chns=CHNS, mid_ch: int = MID_CH,
+                 interm_ch: int = INTERM_CH):
     """[(cout, cin, stride)] of the 16 convs of DenBlock `block` (0 = temp1, 1 = temp2).
     in_ch=3 is the blind variant (InputCvBlock(blind=True), bsvd_arch.py:204-205)."""
-    c0, c1, c2 = CHNS
-    cin = in_ch if block == 0 else MID_CH
-    cout = MID_CH if block == 0 else OUT_CH
+    c0, c1, c2 = chns
+    cin = in_ch if block == 0 else mid_ch
+    cout = mid_ch if block == 0 else OUT_CH
+    INTERM_CH = interm_ch  # noqa: N806
     return [
         (INTERM_CH, cin, 1), (c0, INTERM_CH, 1),
         (c1, c0, 2), (c1, c1, 1), (c1, c1, 1),
@@ -96,7 +104,8 @@ def bsvd_keys():
 
 
 def make_synthetic_params(seed: int = 0, weight_scale: float = 0.5, prefix: str = "base_model.",
-                          in_ch: int = IN_CH):
+                          in_ch: int = IN_CH, chns=CHNS, mid_ch: int = MID_CH,
+                          interm_ch: int = INTERM_CH, act: str = "relu6"):
     """Seeded synthetic checkpoint in the TSN key layout (SURVEY §8d recipe).
 
     kaiming_normal_(nonlinearity='relu') statistics (wnet_models.py:155-162: std = sqrt(2/fan_in))
@@ -107,7 +116,7 @@ def make_synthetic_params(seed: int = 0, weight_scale: float = 0.5, prefix: str 
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
     for blk in range(2):
-        for name, (co, ci, _s) in zip(_TSN_LAYER_KEYS, layer_shapes(blk, in_ch)):
+        for name, (co, ci, _s) in zip(_TSN_LAYER_KEYS, layer_shapes(blk, in_ch, chns, mid_ch, interm_ch)):
             fan_in = ci * 9
             w = rng.standard_normal((co, ci, 3, 3), dtype=np.float32) * np.float32(
                 weight_scale * np.sqrt(2.0 / fan_in))
@@ -173,6 +182,15 @@ def _relu6(x):
     return x.clamp(0.0, 6.0)  # nn.ReLU6, bsvd_arch.py:185-192 with act='relu6'
 
 
+def _act_fn(act: str):
+    """get_act_function (bsvd_arch.py:185-192): 'relu' -> nn.ReLU, 'relu6' -> nn.ReLU6."""
+    if act == "relu6":
+        return _relu6
+    if act == "relu":
+        return lambda t: t.clamp_min(0.0)
+    raise ValueError(act)
+
+
 def temporal_shift(x):
     """batch_shift with an empty past buffer (temporal_shift.py:53-80, batch_index=-1) ==
     ShiftConv's concat (bsvd_arch.py:42-50) over a whole clip [T,C,H,W]."""
@@ -184,11 +202,12 @@ def temporal_shift(x):
     return out
 
 
-def denblock_clip(layers, x, op_dtype=None, store_dtype=None):
+def denblock_clip(layers, x, op_dtype=None, store_dtype=None, act: str = "relu6"):
     """DenBlock.forward over all frames at once (wnet_models.py:164-183 with TemporalShift in front
     of every CvBlock conv, tsm_arch.py:49-57).  layers: 16 (w,b).  x: [T,Cin,H,W]."""
     L = lambda i, t, stride=1: _conv(t, layers[i][0], layers[i][1], stride, op_dtype)  # noqa: E731
     st = lambda t: _rnd(t, store_dtype)  # noqa: E731
+    _relu6 = _act_fn(act)  # noqa: F811  (the block's activation, 'relu6' for BSVD-64)
     x0 = st(_relu6(L(0, x)))
     x0 = st(_relu6(L(1, x0)))
     x1 = st(_relu6(L(2, x0, 2)))
@@ -211,12 +230,12 @@ def denblock_clip(layers, x, op_dtype=None, store_dtype=None):
     return y
 
 
-def forward_clip(layers, x, op_dtype=None, store_dtype=None):
+def forward_clip(layers, x, op_dtype=None, store_dtype=None, act: str = "relu6"):
     """BSVD.forward on ONE stream x: [T,4,H,W] -> [T,3,H,W] (clip order; same arithmetic as the
     streaming order).  op_dtype/store_dtype=None is the exact fp32 oracle."""
     with torch.no_grad():
-        mid = _rnd(denblock_clip(layers[:16], x, op_dtype, store_dtype), store_dtype)
-        return denblock_clip(layers[16:], mid, op_dtype, store_dtype)
+        mid = _rnd(denblock_clip(layers[:16], x, op_dtype, store_dtype, act), store_dtype)
+        return denblock_clip(layers[16:], mid, op_dtype, store_dtype, act)
 
 
 # ------------------------------------------------------------------------------------------------

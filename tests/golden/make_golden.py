@@ -68,6 +68,37 @@ class cpu_shim:
         torch.Tensor.cuda = self._cuda
 
 
+def main_c32(REG, gqb, out_dir):
+    """The blind c32 configuration of options/train/0402_*_blind_c32.yml (net2d_opt :63-68), clip
+    order through the reference's TSN class (its streaming class cannot run blind models whose
+    mid_ch is not 3, bsvd_arch.py:449-452)."""
+    cfg = O.C32
+    net2d = dict(chns=list(cfg["chns"]), mid_ch=cfg["mid_ch"], shift_input=False, norm="none", blind=True)
+    for name, T, H, W, pseed, scale, cseed in [("c32_blind_T5_24x40", 5, 24, 40, 7, 0.5, 9),
+                                               ("c32_blind_T2_16x132", 2, 16, 132, 8, 0.5, 10)]:
+        sd = O.make_synthetic_params(pseed, scale, in_ch=3, chns=cfg["chns"], mid_ch=cfg["mid_ch"],
+                                     interm_ch=cfg["interm_ch"])
+        tsn = REG.get("TSN")(num_segments=11, base_model="WNet_multistage", shift_type="TSM",
+                             shift_div=8, inplace=False, net2d_opt=net2d).eval()
+        assert sorted(tsn.state_dict().keys()) == sorted(sd.keys()), "TSN key layout mismatch"
+        tsn.load_state_dict(sd, strict=True)
+        x, _ = O.make_synthetic_clip(T, H, W, cseed)
+        gqb._init(0)
+        with torch.no_grad():
+            y_tsn = tsn(x[None, :, :3])[0]
+        gqb._clean()
+        mine = O.forward_clip(O.layers_from_tsn_state(sd), x[:, :3], act=cfg["act"])
+        d = float((y_tsn - mine).abs().max())
+        print(f"{name}: reference TSN vs oracle max-abs {d:.3e}; |y|max {float(y_tsn.abs().max()):.3f}")
+        assert d < 2e-4, d
+        np.savez_compressed(
+            os.path.join(out_dir, name + ".npz"), T=T, H=H, W=W, param_seed=pseed, weight_scale=scale,
+            clip_seed=cseed, params_digest=O.params_digest(sd), x_digest=O.params_digest({"x": x}),
+            y_clip=y_tsn.numpy().astype(np.float32),
+            n_params=sum(p.numel() for p in tsn.parameters()),
+            reference_commit="29a6f05", torch_version=torch.__version__)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -75,6 +106,9 @@ def main():
     net2d = dict(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm="none", interm_ch=64,
                  act="relu6")
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    if os.environ.get("GOLDEN_ONLY") == "c32":
+        return main_c32(REG, gqb, out_dir)
+    main_c32(REG, gqb, out_dir)
     for name, T, H, W, pseed, scale, cseed in CASES:
         sd = O.make_synthetic_params(pseed, scale)
         tsn = REG.get("TSN")(num_segments=11, base_model="WNet_multistage", shift_type="TSM",

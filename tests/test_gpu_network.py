@@ -16,7 +16,9 @@ import torch
 from oracle import bsvd_oracle as O
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith("c32_")]
+GOLDEN_C32 = [p for p in _ALL if os.path.basename(p).startswith("c32_")]
 TOL = {"fp16": 1e-3, "bf16": 1e-2}
 
 

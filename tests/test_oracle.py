@@ -12,7 +12,9 @@ import torch
 
 from oracle import bsvd_oracle as O
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith("c32_")]      # BSVD-64, clip + stream
+GOLDEN_C32 = [p for p in _ALL if os.path.basename(p).startswith("c32_")]      # blind c32, clip (TSN)
 
 
 def _load(path):
@@ -55,6 +57,20 @@ def test_stream_order_matches_reference(path):
     first = next(i for i, o in enumerate(outs) if o is not None)
     assert first == int(g["first_output_call"]) == O.StreamOracle.shift_num == int(g["shift_num"])
     assert calls == int(g["calls_to_drain"])
+
+
+@pytest.mark.parametrize("path", GOLDEN_C32, ids=[os.path.basename(p)[:-4] for p in GOLDEN_C32])
+def test_c32_blind_clip_matches_reference(path):
+    """The blind c32 configuration (options/train/0402_*_blind_c32.yml: chns [32,64,128], mid_ch 32,
+    interm_ch 30, act 'relu') against the reference TSN's output."""
+    g = np.load(path)
+    c = O.C32
+    sd = O.make_synthetic_params(int(g["param_seed"]), float(g["weight_scale"]), in_ch=3,
+                                 chns=c["chns"], mid_ch=c["mid_ch"], interm_ch=c["interm_ch"])
+    assert O.params_digest(sd) == str(g["params_digest"])
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    y = O.forward_clip(O.layers_from_tsn_state(sd), x[:, :3], act=c["act"])
+    assert float((y - torch.from_numpy(g["y_clip"])).abs().max()) <= 1e-4
 
 
 def test_param_count_and_keys():
