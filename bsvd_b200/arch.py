@@ -76,16 +76,19 @@ class BSVD(nn.Module):
                  pretrain_ckpt='./experiments/pretrained_ckpt/bsvd-64.pth', precision=None):
         super().__init__()
         chns = list(chns)
-        if not (chns == [64, 128, 256] and mid_ch == 64 and interm_ch == 64 and in_ch == 4 and
-                out_ch == 3 and norm == 'none' and act == 'relu6' and not shift_input):
+        if not (chns in ([64, 128, 256], [32, 64, 128]) and 3 <= mid_ch <= 64 and 1 <= interm_ch <= 64
+                and in_ch == 4 and out_ch == 3 and norm == 'none' and act in ('relu6', 'relu')
+                and not shift_input):
             raise NotImplementedError(
-                "bsvd_b200 implements the BSVD-64 configuration of options/test/bsvd_c64.yml only "
-                "(chns=[64,128,256], mid_ch=64, interm_ch=64, norm='none', act='relu6', "
-                "shift_input=False; blind=True is supported); there is no CPU/PyTorch fallback")
+                "bsvd_b200 implements chns=[64,128,256] (options/test/bsvd_c64.yml) and [32,64,128] "
+                "(options/train/0402_*_c32.yml; zero-padded to the 64-channel kernels) with "
+                "mid_ch<=64, interm_ch<=64, norm='none', act='relu6'|'relu', shift_input=False "
+                "(blind=True is supported); there is no CPU/PyTorch fallback")
         if blind:
             in_ch = 3      # InputCvBlock(blind=True) drops the noise-map channel (bsvd_arch.py:204-205)
         self.blind = bool(blind)
-        self.cfg = dict(chns=chns, mid_ch=mid_ch, in_ch=in_ch, out_ch=out_ch, interm_ch=interm_ch)
+        self.cfg = dict(chns=chns, mid_ch=mid_ch, in_ch=in_ch, out_ch=out_ch, interm_ch=interm_ch,
+                        act=act)
         self.temp1 = _Node()
         self.temp2 = _Node()
         self._param_names = []
@@ -173,7 +176,7 @@ class BSVD(nn.Module):
             cfg.chns[0], cfg.chns[1], cfg.chns[2] = self.cfg["chns"]
             cfg.mid_ch, cfg.interm_ch = self.cfg["mid_ch"], self.cfg["interm_ch"]
             cfg.in_ch, cfg.out_ch = self.cfg["in_ch"], self.cfg["out_ch"]
-            cfg.act_relu6, cfg.norm_none = 1, 1
+            cfg.act_relu6, cfg.norm_none = (1 if self.cfg["act"] == "relu6" else 0), 1
             cfg.precision = capi.PREC_FP16 if prec == "fp16" else capi.PREC_BF16
             cfg.device = device.index if device.index is not None else torch.cuda.current_device()
             h = C.c_void_p()

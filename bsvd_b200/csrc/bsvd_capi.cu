@@ -164,14 +164,19 @@ static inline uint16_t to16(float f, int bf16) { return bf16 ? f32_to_bf16(f) : 
 // one fused conv stage: static description + packed weights + launch
 // ------------------------------------------------------------------------------------------------
 struct StageSpec {
-  int cin = 64, cout = 64;   // reference conv channels
+  int cin = 64, cout = 64;   // conv channels as the kernels see them (multiples of 64 except the
+                             // first conv's input and the last conv's output)
+  int cin_l = 0, cout_l = 0; // the reference conv's channels when smaller (c32 configurations run
+                             // zero-padded to the 64-channel kernels); 0 = same as cin / cout
   int stride = 1;
-  bool relu6 = false, pixshuf = false, skip = false, shift = false;
+  bool relu6 = false, relu = false, pixshuf = false, skip = false, shift = false;
   bool resid_in = false, final_out = false, first_im2col = false;
   bool stacked = false;   // 64->64 stride-1 stage with the vertical taps stacked in N (conv_tc.cuh mode 2)
   // derived
   int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
   void derive() {
+    if (!cin_l) cin_l = cin;
+    if (!cout_l) cout_l = cout;
     gemm_n = final_out ? 16 : cout;
     static const int ntile_max = [] { const char* e = getenv("BSVD_B200_NTILE_MAX"); return e ? atoi(e) : 256; }();
     ntile = gemm_n >= 256 ? (ntile_max >= 256 ? 256 : 128) : gemm_n;
@@ -198,10 +203,10 @@ struct StageSpec {
 // GEMM column -> reference output channel (PixelShuffle permutes so that one sub-pixel's channels
 // are contiguous: column q*Cq + c  <-  conv channel c*4 + q, nn.PixelShuffle semantics).
 static inline int col_to_cout(const StageSpec& s, int col) {
-  if (!s.pixshuf) return col;
+  if (!s.pixshuf) return col < s.cout_l ? col : -1;
   const int cq = s.cout / 4;
   const int q = col / cq, c = col % cq;
-  return c * 4 + q;
+  return c < s.cout_l / 4 ? c * 4 + q : -1;     // padded channels of a sub-pixel carry zeros
 }
 
 // Repack OIHW fp32 -> [n_tile][chunk][tap][ntile rows][64 k] 16-bit, each 128-byte row stored with
@@ -212,16 +217,16 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
   bias.assign(s.gemm_n, 0.f);
   for (int col = 0; col < s.gemm_n; ++col) {
     const int co = col_to_cout(s, col);
-    if (co < s.cout) bias[col] = b ? b[co] : 0.f;
+    if (co >= 0 && co < s.cout_l) bias[col] = b ? b[co] : 0.f;
   }
   if (s.final_out) {
     // final_conv.cuh layout: slab dx, row n = dy*3 + co, 64 input channels, SW128-swizzled rows
     for (int dx = 0; dx < 3; ++dx)
       for (int dy = 0; dy < 3; ++dy)
-        for (int co = 0; co < s.cout; ++co) {
+        for (int co = 0; co < s.cout_l; ++co) {
           const int n = dy * 3 + co;
-          for (int k = 0; k < kChunk; ++k) {
-            const float v = w[((size_t)co * s.cin + k) * 9 + dy * 3 + dx];
+          for (int k = 0; k < kChunk && k < s.cin_l; ++k) {
+            const float v = w[((size_t)co * s.cin_l + k) * 9 + dy * 3 + dx];
             pack[((size_t)dx * kFinalN + n) * kChunk + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = to16(v, bf16);
           }
         }
@@ -242,8 +247,9 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
           else if (row < 96) { dy = rank == 0 ? 1 : 0; co = row - 32; local = row - 32; }
           else if (row < 160) { dy = rank == 0 ? 2 : 1; co = row - 96; local = row - 96; }
           else { dy = 2; co = rank * 32 + (row - 160); local = row - 160; }
-          for (int k = 0; k < kChunk; ++k) {
-            const float v = w[((size_t)co * s.cin + k) * 9 + dy * 3 + dx];
+          if (co >= s.cout_l) continue;
+          for (int k = 0; k < kChunk && k < s.cin_l; ++k) {
+            const float v = w[((size_t)co * s.cin_l + k) * 9 + dy * 3 + dx];
             cta[(size_t)row * kChunk + (((k >> 3) ^ (local & 7)) << 3) + (k & 7)] = to16(v, bf16);
           }
         }
@@ -258,17 +264,17 @@ static void pack_weights(const StageSpec& s, const float* w, const float* b, int
             ((size_t)(nt * s.cin_chunks + c) * s.ntaps() + (tap - s.tap_begin)) * s.ntile * kChunk;
         for (int n = 0; n < s.ntile; ++n) {
           const int co = col_to_cout(s, nt * s.ntile + n);
-          if (co >= s.cout) continue;
+          if (co < 0 || co >= s.cout_l) continue;
           for (int k = 0; k < kChunk; ++k) {
             float v = 0.f;
             if (s.first_im2col) {
               // K index = tap'*4 + ci: first_conv.cuh builds 4 slots per tap (slot 3 is the noise
               // map, or zero for the blind 3-channel variant)
               const int tp = k / 4, ci = k % 4;
-              if (tp < 9 && ci < s.cin) v = w[((size_t)co * s.cin + ci) * 9 + tp];
+              if (tp < 9 && ci < s.cin_l) v = w[((size_t)co * s.cin_l + ci) * 9 + tp];
             } else {
               const int ci = c * kChunk + k;
-              v = w[((size_t)co * s.cin + ci) * 9 + tap];
+              if (ci < s.cin_l) v = w[((size_t)co * s.cin_l + ci) * 9 + tap];
             }
             const int chunk16 = (k >> 3) ^ (n & 7);
             blk[(size_t)n * kChunk + chunk16 * 8 + (k & 7)] = to16(v, bf16);
@@ -380,15 +386,16 @@ static int launch_pipe(const StageLaunch& L, cudaStream_t st) {
 }
 // Epilogue feature sets the kernels are specialised for; a stage runs on the smallest set that
 // covers its flags (the single-CTA debug path only has the general instance).
-constexpr int kMaskPlain = EPI_RELU6;
-constexpr int kMaskShift = EPI_RELU6 | EPI_SHIFT;
-constexpr int kMaskResid = EPI_RELU6 | EPI_RESID_IN;
+constexpr int kMaskAct = EPI_RELU6 | EPI_RELU;       // the activation is a run-time flag inside every instance
+constexpr int kMaskPlain = kMaskAct;
+constexpr int kMaskShift = kMaskAct | EPI_SHIFT;
+constexpr int kMaskResid = kMaskAct | EPI_RESID_IN;
 // PixelShuffle stages: the skip add runs on the tensor core (ConvParams::skip_mma), so the
 // epilogue instances carry no skip path
 constexpr int kMaskUpTma = EPI_PIXSHUF | EPI_TMA_OUT;   // upc1.convblock.0: units leave through TMA stores
 constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0 with the skip on the tensor core (opt-in)
 constexpr int kMaskUpSkipShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0: skip added in the epilogue
-constexpr int kMaskAll = EPI_RELU6 | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
+constexpr int kMaskAll = kMaskAct | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
   if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
@@ -460,7 +467,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   // BSVD_B200_SKIP_MMA_SHIFT=1: its MMA time is the bound, not its epilogue)
   static const int up_shift_on = [] { const char* e = getenv("BSVD_B200_SKIP_MMA_SHIFT"); return (e && e[0] == '1') ? 1 : 0; }();
   const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
-                        !s.first_im2col && !s.final_out && (!s.shift || up_shift_on);
+                        !s.first_im2col && !s.final_out && (!s.shift || up_shift_on) &&
+                        s.cin_chunks * s.ntaps() >= 4 * (s.ntile / 64);   // one skip block per four slabs
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
   static const int tma_shift_on = [] { const char* e = getenv("BSVD_B200_TMA_SHIFT"); return e ? atoi(e) : 0; }();   // measured: -3 % when on
   const bool tma_out = tma_on && cta2 && (!s.shift || (tma_shift_on && !s.pixshuf)) &&
@@ -485,7 +493,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.positions = p.T * p.yblocks * p.xblocks;
     p.total_tiles = p.positions;
     p.wpack = sd.wpack; p.bias = sd.bias;
-    p.flags = EPI_RELU6 | (bf16 ? EPI_BF16 : 0);
+    p.flags = (s.relu ? EPI_RELU : EPI_RELU6) | (bf16 ? EPI_BF16 : 0);
     p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = 6;
     p.out_frame_stride = (long long)Ho * Wo * s.cout;
     L->cta2 = 0;
@@ -557,6 +565,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.bias = sd.bias;
   int flags = 0;
   if (s.relu6) flags |= EPI_RELU6;
+  if (s.relu) flags |= EPI_RELU;
   if (s.pixshuf) flags |= EPI_PIXSHUF;
   if (s.skip && !skip_mma) flags |= EPI_SKIP;
   if (s.shift) flags |= EPI_SHIFT;
@@ -714,6 +723,7 @@ static const int kBlockDelay = 8;   // latency of one DenBlock in steps (8 BiBuf
 struct bsvd_handle {
   bsvd_config cfg;
   int bf16 = 0;
+  int cp[3] = {64, 128, 256};   // channels of the full / half / quarter resolution tensors as stored
   StageDev stages[BSVD_NUM_LAYERS];
   // ---- clip-mode workspace / plan (rebuilt when T,H,W change) ----
   int pT = 0, pH = 0, pW = 0, p_inc = 0;
@@ -761,33 +771,49 @@ struct bsvd_handle {
   } stream;
 };
 
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 static void build_specs(bsvd_handle* h) {
-  // DenBlock (bsvd_arch.py:325-396), BSVD-64: chns 64/128/256; temp1 4->64, temp2 64->3.
+  // DenBlock (bsvd_arch.py:325-396).  BSVD-64: chns 64/128/256, temp1 4->64, temp2 64->3.  The c32
+  // configurations (chns 32/64/128, interm_ch 30, mid_ch 32) run on the same kernels with every
+  // channel count below 64 zero-padded to 64 (weights, bias and hence activations of the padded
+  // channels are exactly zero; ReLU keeps them there).
   for (int blk = 0; blk < 2; ++blk) {
     auto S = [&](int l) -> StageSpec& { return h->stages[blk * 16 + l].spec; };
-    const int c0 = h->cfg.chns[0], c1 = h->cfg.chns[1], c2 = h->cfg.chns[2];
+    const int c0 = h->cfg.chns[0], c1 = h->cfg.chns[1], c2 = h->cfg.chns[2], ci = h->cfg.interm_ch;
     const int in_ch = blk == 0 ? h->cfg.in_ch : h->cfg.mid_ch;
     const int out_ch = blk == 0 ? h->cfg.mid_ch : h->cfg.out_ch;
-    S(0) = StageSpec(); S(0).cin = in_ch; S(0).cout = h->cfg.interm_ch; S(0).relu6 = true;
-    S(0).first_im2col = (blk == 0);
-    S(1) = StageSpec(); S(1).cin = h->cfg.interm_ch; S(1).cout = c0; S(1).relu6 = true;
-    S(2) = StageSpec(); S(2).cin = c0; S(2).cout = c1; S(2).stride = 2; S(2).relu6 = true; S(2).shift = true;
-    S(3) = StageSpec(); S(3).cin = c1; S(3).cout = c1; S(3).relu6 = true; S(3).shift = true;
-    S(4) = StageSpec(); S(4).cin = c1; S(4).cout = c1; S(4).relu6 = true;
-    S(5) = StageSpec(); S(5).cin = c1; S(5).cout = c2; S(5).stride = 2; S(5).relu6 = true; S(5).shift = true;
-    S(6) = StageSpec(); S(6).cin = c2; S(6).cout = c2; S(6).relu6 = true; S(6).shift = true;
-    S(7) = StageSpec(); S(7).cin = c2; S(7).cout = c2; S(7).relu6 = true; S(7).shift = true;
-    S(8) = StageSpec(); S(8).cin = c2; S(8).cout = c2; S(8).relu6 = true; S(8).shift = true;
-    S(9) = StageSpec(); S(9).cin = c2; S(9).cout = c2; S(9).relu6 = true;
-    S(10) = StageSpec(); S(10).cin = c2; S(10).cout = c1 * 4; S(10).pixshuf = true; S(10).skip = true; S(10).shift = true;
-    S(11) = StageSpec(); S(11).cin = c1; S(11).cout = c1; S(11).relu6 = true; S(11).shift = true;
-    S(12) = StageSpec(); S(12).cin = c1; S(12).cout = c1; S(12).relu6 = true;
-    S(13) = StageSpec(); S(13).cin = c1; S(13).cout = c0 * 4; S(13).pixshuf = true; S(13).skip = true;
-    S(14) = StageSpec(); S(14).cin = c0; S(14).cout = c0; S(14).relu6 = true;
-    S(15) = StageSpec(); S(15).cin = c0; S(15).cout = out_ch;
+    const bool r6 = h->cfg.act_relu6 != 0;
+    // (layer, logical cin, logical cout): physical = padded to 64, PixelShuffle convs per sub-pixel
+    auto set = [&](int l, int cin, int cout, bool act, bool ps = false) {
+      StageSpec& s = S(l);
+      s = StageSpec();
+      s.cin_l = cin; s.cout_l = cout;
+      s.cin = pad64(cin);
+      s.cout = ps ? 4 * pad64(cout / 4) : pad64(cout);
+      s.relu6 = act && r6; s.relu = act && !r6; s.pixshuf = ps;
+    };
+    set(0, in_ch, ci, true);
+    if (blk == 0) { S(0).first_im2col = true; S(0).cin = in_ch; }     // raw 3/4-channel input
+    set(1, ci, c0, true);
+    set(2, c0, c1, true); S(2).stride = 2; S(2).shift = true;
+    set(3, c1, c1, true); S(3).shift = true;
+    set(4, c1, c1, true);
+    set(5, c1, c2, true); S(5).stride = 2; S(5).shift = true;
+    set(6, c2, c2, true); S(6).shift = true;
+    set(7, c2, c2, true); S(7).shift = true;
+    set(8, c2, c2, true); S(8).shift = true;
+    set(9, c2, c2, true);
+    set(10, c2, c1 * 4, false, true); S(10).skip = true; S(10).shift = true;
+    set(11, c1, c1, true); S(11).shift = true;
+    set(12, c1, c1, true);
+    set(13, c1, c0 * 4, false, true); S(13).skip = true;
+    set(14, c0, c0, true);
+    set(15, c0, out_ch, false);
     S(15).resid_in = (blk == 0); S(15).final_out = (blk == 1);
+    if (blk == 1) S(15).cout = out_ch;                                // 3 output planes, no padding
     for (int l = 0; l < 16; ++l) S(l).derive();
   }
+  h->cp[0] = pad64(h->cfg.chns[0]); h->cp[1] = pad64(h->cfg.chns[1]); h->cp[2] = pad64(h->cfg.chns[2]);
 }
 
 extern "C" { static void free_stream(bsvd_handle* h); }
@@ -805,9 +831,9 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
   if (same_shape && !h->plan.empty()) return 0;   // in/out pointers are patched at launch time
   if (!same_shape) {
     free_workspace(h);
-    const size_t full = (size_t)T * H * W * 64 * 2;
-    const size_t half = (size_t)T * (H / 2) * (W / 2) * 128 * 2;
-    const size_t quar = (size_t)T * (H / 4) * (W / 4) * 256 * 2;
+    const size_t full = (size_t)T * H * W * h->cp[0] * 2;
+    const size_t half = (size_t)T * (H / 2) * (W / 2) * h->cp[1] * 2;
+    const size_t quar = (size_t)T * (H / 4) * (W / 4) * h->cp[2] * 2;
     const size_t fa = align_up(full, 1024), ha = align_up(half, 1024), qa = align_up(quar, 1024);
     const size_t sa = align_up((size_t)T * H * W * 4 * 2, 1024);
     h->ws_bytes = 4 * fa + 3 * ha + 2 * qa + sa;
@@ -828,7 +854,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
   h->p_in = in; h->p_nmap = nmap; h->p_out = out; h->p_inc = in_c;
   h->plan.assign(BSVD_NUM_LAYERS, StageLaunch());
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
-  const long long fs_full = (long long)H * W * 64, fs_half = (long long)H2 * W2 * 128;
+  const long long fs_full = (long long)H * W * h->cp[0], fs_half = (long long)H2 * W2 * h->cp[1];
   for (int blk = 0; blk < 2; ++blk) {
     auto plan = [&](int l, const void* src, int sh, int sw, void* dst, const void* skip = nullptr,
                     int skip_C = 0, long long skip_fs = 0) -> int {
@@ -850,10 +876,10 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     rc |= plan(7, h->bufQ1, H4, W4, h->bufQ0);
     rc |= plan(8, h->bufQ0, H4, W4, h->bufQ1);
     rc |= plan(9, h->bufQ1, H4, W4, h->bufQ0);
-    rc |= plan(10, h->bufQ0, H4, W4, h->bufH0, h->bufX1, 128, fs_half);
+    rc |= plan(10, h->bufQ0, H4, W4, h->bufH0, h->bufX1, h->cp[1], fs_half);
     rc |= plan(11, h->bufH0, H2, W2, h->bufH1);
     rc |= plan(12, h->bufH1, H2, W2, h->bufH0);
-    rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, 64, fs_full);
+    rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, h->cp[0], fs_full);
     rc |= plan(14, h->bufA, H, W, h->bufP);
     if (blk == 0) rc |= plan(15, h->bufP, H, W, h->bufM);
     else rc |= plan(15, h->bufP, H, W, out, h->bufS, 4, (long long)H * W * 4);
@@ -886,12 +912,15 @@ const char* bsvd_version(void) { return "bsvd_b200 0.1 (sm_100a, tcgen05/TMEM/TM
 
 int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
   if (!cfg || !out) return fail("null argument");
-  if (!(cfg->chns[0] == 64 && cfg->chns[1] == 128 && cfg->chns[2] == 256 && cfg->mid_ch == 64 &&
-        cfg->interm_ch == 64 && (cfg->in_ch == 4 || cfg->in_ch == 3) && cfg->out_ch == 3 &&
-        cfg->act_relu6 == 1 && cfg->norm_none == 1))
-    return fail("only the BSVD-64 configuration of options/test/bsvd_c64.yml is implemented on the "
-                "GPU path (chns=[64,128,256], mid_ch=64, interm_ch=64, in_ch=4 (or 3 = blind), "
-                "out_ch=3, norm='none', act='relu6'); there is no CPU fallback");
+  const bool c64 = cfg->chns[0] == 64 && cfg->chns[1] == 128 && cfg->chns[2] == 256;
+  const bool c32 = cfg->chns[0] == 32 && cfg->chns[1] == 64 && cfg->chns[2] == 128;
+  if (!((c64 || c32) && cfg->mid_ch >= 3 && cfg->mid_ch <= 64 && cfg->interm_ch >= 1 &&
+        cfg->interm_ch <= 64 && (cfg->in_ch == 4 || cfg->in_ch == 3) && cfg->out_ch == 3 &&
+        (cfg->act_relu6 == 0 || cfg->act_relu6 == 1) && cfg->norm_none == 1))
+    return fail("implemented on the GPU path: chns=[64,128,256] (options/test/bsvd_c64.yml) or "
+                "[32,64,128] (options/train/0402_*_c32.yml, zero-padded to the 64-channel kernels), "
+                "mid_ch<=64, interm_ch<=64, in_ch=4 (or 3 = blind), out_ch=3, norm='none', "
+                "act='relu6'|'relu'; there is no CPU fallback");
   if (cfg->precision != BSVD_PREC_FP16 && cfg->precision != BSVD_PREC_BF16)
     return fail("unknown precision %d", cfg->precision);
   int ndev = 0;
@@ -937,8 +966,8 @@ int bsvd_destroy(bsvd_handle* h) {
 int bsvd_layer_shape(const bsvd_handle* h, int layer, int* out_ch, int* in_ch, int* stride) {
   if (!h || layer < 0 || layer >= BSVD_NUM_LAYERS) return fail("bad layer index %d", layer);
   const StageSpec& s = h->stages[layer].spec;
-  if (out_ch) *out_ch = s.cout;
-  if (in_ch) *in_ch = s.cin;
+  if (out_ch) *out_ch = s.cout_l;
+  if (in_ch) *in_ch = s.cin_l;
   if (stride) *stride = s.stride;
   return 0;
 }
@@ -948,9 +977,9 @@ int bsvd_set_weights(bsvd_handle* h, int layer, const float* w, const float* bia
   if (!h || layer < 0 || layer >= BSVD_NUM_LAYERS) return fail("bad layer index %d", layer);
   if (!w) return fail("null weight pointer");
   StageDev& sd = h->stages[layer];
-  if (sd.spec.cout != out_ch || sd.spec.cin != in_ch)
-    return fail("layer %d expects weight [%d,%d,3,3], got [%d,%d,3,3]", layer, sd.spec.cout,
-                sd.spec.cin, out_ch, in_ch);
+  if (sd.spec.cout_l != out_ch || sd.spec.cin_l != in_ch)
+    return fail("layer %d expects weight [%d,%d,3,3], got [%d,%d,3,3]", layer, sd.spec.cout_l,
+                sd.spec.cin_l, out_ch, in_ch);
   return upload_stage(sd, w, bias, h->bf16);
 }
 
@@ -981,8 +1010,8 @@ int bsvd_stage_info(const bsvd_handle* h, int stage, int* cin, int* cout, int* s
                     int* rows) {
   if (!h || stage < 1 || stage > BSVD_NUM_LAYERS) return fail("bad stage index %d", stage);
   const StageSpec& s = h->stages[stage - 1].spec;
-  if (cin) *cin = s.cin;
-  if (cout) *cout = s.cout;
+  if (cin) *cin = s.cin_l;
+  if (cout) *cout = s.cout_l;
   if (stride) *stride = s.stride;
   if (ntile) *ntile = s.ntile;
   if (rows) *rows = s.rows;
@@ -1190,9 +1219,9 @@ static void free_stream(bsvd_handle* h) {
   S = bsvd_handle::Stream();
 }
 
-static size_t ring_slot_bytes(int ring, int H, int W) {
+static size_t ring_slot_bytes(const bsvd_handle* h, int ring, int H, int W) {
   const int r = kRingRes[ring];
-  const int C = (r == 1) ? 64 : (r == 2 ? 128 : 256);
+  const int C = (r == 1) ? h->cp[0] : (r == 2 ? h->cp[1] : h->cp[2]);
   return align_up((size_t)(H / r) * (W / r) * C * 2, 1024);
 }
 
@@ -1203,7 +1232,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
   S.H = H; S.W = W;
   size_t total = 0;
   for (int b = 0; b < 2; ++b)
-    for (int k = 0; k < kNumRings; ++k) total += ring_slot_bytes(k, H, W) * kRingSlots[k];
+    for (int k = 0; k < kNumRings; ++k) total += ring_slot_bytes(h, k, H, W) * kRingSlots[k];
   const size_t raw_bytes = align_up((size_t)9 * 4 * H * W * sizeof(float), 1024);
   total += raw_bytes;
   const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
@@ -1214,7 +1243,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
   S.raw = reinterpret_cast<float*>(p); p += raw_bytes;
   S.aux = p; p += 9 * aux_slot;
   for (int b = 0; b < 2; ++b)
-    for (int k = 0; k < kNumRings; ++k) { S.ring[b][k] = p; p += ring_slot_bytes(k, H, W) * kRingSlots[k]; }
+    for (int k = 0; k < kNumRings; ++k) { S.ring[b][k] = p; p += ring_slot_bytes(h, k, H, W) * kRingSlots[k]; }
   for (int b = 0; b < 2; ++b)
     for (int l = 0; l < 16; ++l) {
       auto& SL = S.layers[b * 16 + l];
@@ -1223,7 +1252,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
       const int in_blk = (b == 1 && l == 0) ? 0 : b;
       const int r = kRingRes[in_ring];
-      const size_t in_bytes = ring_slot_bytes(in_ring, H, W);
+      const size_t in_bytes = ring_slot_bytes(h, in_ring, H, W);
       StageIO io;
       io.T = 1; io.H = H / r; io.W = W / r;
       io.in = S.ring[in_blk][in_ring];
@@ -1231,14 +1260,14 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       io.ring_mode = sd.spec.shift ? 1 : 0;
       io.zero_future = sd.spec.shift ? 1 : 0;
       io.out_next = io.out;                      // placeholders so plan_stage's checks pass
-      io.skip = S.ring[b][kRingX0]; io.skip_C = 64;
+      io.skip = S.ring[b][kRingX0]; io.skip_C = h->cp[0];
       io.resid_in = S.raw; io.resid_C = 4;
-      io.skip_T = kRingSlots[kRingX0]; io.skip_T_stride = (long long)ring_slot_bytes(kRingX0, H, W);
+      io.skip_T = kRingSlots[kRingX0]; io.skip_T_stride = (long long)ring_slot_bytes(h, kRingX0, H, W);
       if (l == 10) {
-        io.skip = S.ring[b][kRingX1]; io.skip_C = 128;
-        io.skip_T = kRingSlots[kRingX1]; io.skip_T_stride = (long long)ring_slot_bytes(kRingX1, H, W);
+        io.skip = S.ring[b][kRingX1]; io.skip_C = h->cp[1];
+        io.skip_T = kRingSlots[kRingX1]; io.skip_T_stride = (long long)ring_slot_bytes(h, kRingX1, H, W);
       }
-      io.out_T = kRingSlots[kLayerOut[l]]; io.out_T_stride = (long long)ring_slot_bytes(kLayerOut[l], H, W);
+      io.out_T = kRingSlots[kLayerOut[l]]; io.out_T_stride = (long long)ring_slot_bytes(h, kLayerOut[l], H, W);
       if (l == 15 && b == 1) { io.skip = S.aux; io.skip_C = 4; }
       if (l == 15 && b == 0) io.aux_out = S.aux;
       if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
@@ -1294,7 +1323,7 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
       const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
       L.map = SL.maps[f % kRingSlots[in_ring]];
       const int oring = kLayerOut[l];
-      const size_t ob = ring_slot_bytes(oring, H, W);
+      const size_t ob = ring_slot_bytes(h, oring, H, W);
       auto oslot = [&](long long ff) { return S.ring[b][oring] + (size_t)(ff % kRingSlots[oring]) * ob; };
       ConvParams& p = L.p;
       p.out = oslot(f);
@@ -1305,11 +1334,11 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
       p.out_t0 = (int)(f % kRingSlots[oring]);     // TMA stores address the ring through map_o
       if (l == 10) {
         p.skip_t0 = (int)(f % kRingSlots[kRingX1]);   // skip add on the tensor core: ring slot of map_s
-        p.skip = S.ring[b][kRingX1] + (size_t)p.skip_t0 * ring_slot_bytes(kRingX1, H, W);
+        p.skip = S.ring[b][kRingX1] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX1, H, W);
       }
       if (l == 13) {
         p.skip_t0 = (int)(f % kRingSlots[kRingX0]);
-        p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(kRingX0, H, W);
+        p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX0, H, W);
       }
       const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
       if (l == 0 && b == 0) {

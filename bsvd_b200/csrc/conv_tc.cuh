@@ -53,7 +53,8 @@ enum : int {
   EPI_FINAL = 32,       // temp2 outc.3 (final_conv.cuh): fp32 NCHW out = skip[:, :3] - conv[:, :3]
   EPI_BF16 = 64,        // 16-bit storage type is bf16 (else fp16)
   EPI_ZERO_FUTURE = 128, // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
-  EPI_TMA_OUT = 256     // compile-time only: units leave through cp.async.bulk.tensor stores
+  EPI_TMA_OUT = 256,    // compile-time only: units leave through cp.async.bulk.tensor stores
+  EPI_RELU = 512        // nn.ReLU (act='relu', the c32 configurations) instead of nn.ReLU6
 };
 
 struct ConvParams {
@@ -421,6 +422,18 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 // --------------------------------------------------------------------------------------------
 // packed ReLU6 on two 16-bit values: clamp(round(x)) == round(clamp(x)) because 0 and 6 are exact
 template <bool BF16>
+__device__ __forceinline__ uint32_t relu_packed(uint32_t u) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+    h = __hmax2(h, __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    h = __hmax2(h, __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool BF16>
 __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
   if constexpr (BF16) {
     __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
@@ -599,6 +612,9 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       if (flags & EPI_RELU6) {
         o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
         o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
+      } else if (flags & EPI_RELU) {
+        o[j].x = relu_packed<BF16>(o[j].x); o[j].y = relu_packed<BF16>(o[j].y);
+        o[j].z = relu_packed<BF16>(o[j].z); o[j].w = relu_packed<BF16>(o[j].w);
       }
     }
     if constexpr ((MASK & EPI_TMA_OUT) != 0) {

@@ -180,7 +180,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile<kFirstR>(p, tile);
-      EpiLane el = epi_lane<EPI_RELU6>(p, lane);
+      EpiLane el = epi_lane<EPI_RELU6 | EPI_RELU>(p, lane);
       el.nvalid = min(32, p.W - (tc.x0 + quad * 32));
       const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(acc_full(buf), acc_phase);
@@ -196,7 +196,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
-      constexpr int kEpiMask = EPI_RELU6 | EPI_TMA_OUT;
+      constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
       float bv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[(u0 % G) * 32 + i];

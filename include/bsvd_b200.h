@@ -30,8 +30,10 @@ typedef struct bsvd_handle bsvd_handle;
 enum { BSVD_PREC_FP16 = 0, BSVD_PREC_BF16 = 1 };
 
 /* Mirrors the constructor kwargs of BSVD (bsvd_arch.py:446-447) as passed by
- * options/test/bsvd_c64.yml:85-93.  Only the BSVD-64 configuration is implemented on the GPU:
- * chns={64,128,256}, mid_ch=64, interm_ch=64, in_ch=4, out_ch=3, norm='none', act='relu6'.
+ * options/test/bsvd_c64.yml:85-93: chns={64,128,256}, mid_ch=64, interm_ch=64, in_ch=4 (3 = blind),
+ * out_ch=3, norm='none', act='relu6'.  Also accepted: the c32 configurations
+ * (options/train/0402_*_blind_c32.yml:63-68: chns={32,64,128}, mid_ch=32, interm_ch=30, act='relu'),
+ * which run on the same kernels with channel counts below 64 zero-padded to 64.
  * Anything else makes bsvd_create fail (there is no CPU fallback). */
 typedef struct bsvd_config {
   int chns[3];
@@ -39,7 +41,7 @@ typedef struct bsvd_config {
   int interm_ch;
   int in_ch;
   int out_ch;
-  int act_relu6;   /* 1 = relu6 (only supported value) */
+  int act_relu6;   /* 1 = relu6 (bsvd_c64.yml), 0 = relu (the c32 configurations) */
   int norm_none;   /* 1 = norm 'none' (only supported value) */
   int precision;   /* BSVD_PREC_* */
   int device;      /* CUDA device ordinal, -1 = current */

@@ -50,12 +50,13 @@ def test_create_rejects_other_configs():
     import ctypes as C
     lib = capi.load_library()
     cfg = capi.BsvdConfig()
-    cfg.chns[0], cfg.chns[1], cfg.chns[2] = 32, 64, 128
-    cfg.mid_ch, cfg.interm_ch = 64, 30
-    cfg.in_ch, cfg.out_ch, cfg.act_relu6, cfg.norm_none, cfg.device = 4, 3, 1, 1, -1
-    h = C.c_void_p()
-    assert lib.bsvd_create(C.byref(cfg), C.byref(h)) != 0
-    assert b"BSVD-64" in lib.bsvd_last_error()
+    for chns, norm_none in (((16, 32, 64), 1), ((64, 128, 256), 0), ((64, 128, 512), 1)):
+        cfg.chns[0], cfg.chns[1], cfg.chns[2] = chns
+        cfg.mid_ch, cfg.interm_ch = 64, 30
+        cfg.in_ch, cfg.out_ch, cfg.act_relu6, cfg.norm_none, cfg.device = 4, 3, 1, norm_none, -1
+        h = C.c_void_p()
+        assert lib.bsvd_create(C.byref(cfg), C.byref(h)) != 0
+        assert b"no CPU fallback" in lib.bsvd_last_error()
 
 
 def _net(**kw):
@@ -95,11 +96,18 @@ def test_module_state_dict_roundtrip_and_half():
 
 def test_module_rejects_unsupported_configs():
     with pytest.raises(NotImplementedError):
-        _net(chns=[32, 64, 128], interm_ch=30)
+        _net(chns=[16, 32, 64], interm_ch=30)
     with pytest.raises(NotImplementedError):
-        _net(act='relu')
+        _net(act='leaky')
     with pytest.raises(NotImplementedError):
         _net(norm='bn')
+    with pytest.raises(NotImplementedError):
+        _net(shift_input=True)
+    # the c32 configurations of options/train/0402_*_c32.yml construct (same parameter names)
+    n32 = _net(chns=[32, 64, 128], mid_ch=32, interm_ch=30, act='relu', blind=True)
+    assert n32.state_dict()["temp1.inc.convblock.0.weight"].shape == (30, 3, 3, 3)
+    assert n32.state_dict()["temp2.inc.convblock.0.weight"].shape == (30, 32, 3, 3)
+    assert n32.state_dict()["temp1.upc1.convblock.0.weight"].shape == (128, 64, 3, 3)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

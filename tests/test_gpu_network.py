@@ -357,6 +357,49 @@ def test_blind_variant_three_channel_input():
         net(x[None].cuda())        # a 4-channel frame is not what a blind model takes
 
 
+def _make_c32(seed, scale, in_ch=3, prec=None, act=None):
+    from bsvd_b200.arch import BSVD
+    c = O.C32
+    act = act or c["act"]
+    sd = O.make_synthetic_params(seed, scale, in_ch=in_ch, chns=c["chns"], mid_ch=c["mid_ch"],
+                                 interm_ch=c["interm_ch"])
+    net = BSVD(chns=list(c["chns"]), mid_ch=c["mid_ch"], shift_input=False, norm='none',
+               interm_ch=c["interm_ch"], act=act, blind=(in_ch == 3), pretrain_ckpt=None, precision=prec)
+    net.load_tsn_state(sd)
+    return net.cuda().eval(), O.layers_from_tsn_state(sd)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("path", GOLDEN_C32, ids=[os.path.basename(p)[:-4] for p in GOLDEN_C32])
+def test_c32_blind_matches_reference_fixture(path, prec):
+    """The blind c32 configuration (options/train/0402_*_blind_c32.yml: chns [32,64,128], mid_ch 32,
+    interm_ch 30, act 'relu') against the output of the reference's TSN class; clip and stream
+    schedules bit-identical to each other."""
+    g = np.load(path)
+    net, _ = _make_c32(int(g["param_seed"]), float(g["weight_scale"]), prec=prec)
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    x3 = x[:, :3].contiguous()
+    with torch.no_grad():
+        y = net(x3[None].cuda())[0]
+        net.reset()
+        outs, _ = _drive_stream(net, x3)
+        net.reset()
+    ref = torch.from_numpy(g["y_clip"])
+    assert float((y.float().cpu() - ref).abs().max()) <= TOL[prec]
+    assert torch.equal(torch.cat([o for o in outs if o is not None]), y)
+    assert net.last_launch_count <= 32
+
+
+def test_c32_with_noise_map_and_relu6_against_oracle():
+    """Non-blind c32 (4-channel input) with act='relu6', a size with partial tiles, vs the oracle."""
+    net, layers = _make_c32(5, 0.5, in_ch=4, act="relu6")
+    x, _ = O.make_synthetic_clip(3, 44, 140, seed=61)
+    with torch.no_grad():
+        y = net(x[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x, act="relu6")
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+
+
 def test_long_clip_crosses_2G_element_offsets():
     """70 frames at 540x960: every full-resolution tensor holds 2.3e9 elements (> 2^31), so frame
     offsets must be 64-bit everywhere.  Property (no oracle at this size): an output frame depends on
