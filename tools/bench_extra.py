@@ -77,6 +77,47 @@ def stream(args):
         "workspace_bytes": None}), flush=True)
 
 
+def c32(args):
+    """The blind c32 configuration (options/train/0402_*_blind_c32.yml) and the fused caller entry
+    (bsvd_denoise_clip) on a [10,3,540,960] clip: frames/s, parity vs the fp32 oracle on 2 frames."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    c = O.C32
+    sd = O.make_synthetic_params(0, 0.5, in_ch=3, chns=c["chns"], mid_ch=c["mid_ch"], interm_ch=c["interm_ch"])
+    net = BSVD(chns=list(c["chns"]), mid_ch=c["mid_ch"], shift_input=False, norm='none',
+               interm_ch=c["interm_ch"], act=c["act"], blind=True, pretrain_ckpt=None,
+               precision=args.precision)
+    net.load_tsn_state(sd)
+    net = net.to(dev).eval()
+    H, W, T = 540, 960, args.frames
+    x, _ = O.make_synthetic_clip(T, H, W, seed=1)
+    x3 = x[:, :3].contiguous().to(dev)
+    lines = []
+    for name, fn in (("c32 forward", lambda: net(x3[None])[0]),
+                     ("c32 denoise_sequence (fused pad/clamp/crop entry)", lambda: net.denoise_sequence(x3, None))):
+        with torch.no_grad():
+            for _ in range(3):
+                y = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                y = fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        lines.append((name, T / ms * 1e3, ms))
+    with torch.no_grad():
+        ys = net(x3[None, :2])[0].float().cpu()
+    ref = O.forward_clip(O.layers_from_tsn_state(sd), x[:2, :3], act=c["act"])
+    for name, fps, ms in lines:
+        print(json.dumps({
+            "metric": "denoised frames/sec at 540x960 (c=32, blind)", "value": fps, "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "dtype": args.precision,
+            "config": {"workload": name + f", 1 clip [1,{T},3,{H},{W}]; zero-padded onto the 64-channel kernels"},
+            "parity": {"max_abs": float((ys - ref).abs().max()), "tolerance": 1e-3}}), flush=True)
+
+
 def tiles(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -133,7 +174,7 @@ def tiles(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["stream", "tiles"])
+    ap.add_argument("mode", choices=["stream", "tiles", "c32"])
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--precision", default=None)
@@ -143,7 +184,11 @@ if __name__ == "__main__":
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
-    if a.mode == "stream":
+    if a.mode == "c32":
+        a.frames = a.frames or 10
+        a.precision = a.precision or "fp16"
+        c32(a)
+    elif a.mode == "stream":
         a.frames = a.frames or 100
         a.precision = a.precision or "bf16"
         stream(a)
