@@ -88,24 +88,41 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       const uint32_t sa = it % kFirstStages, pa = (it / kFirstStages) & 1;
       const TileCoord tc = decode_tile<kFirstR>(p, tile);
       const int x = tc.x0 + i;
-      // 4 input rows (y0-1 .. y0+2) x 3 columns x 4 channels
+      // 4 input rows (y0-1 .. y0+2) x 3 columns x 4 channels.  Row / column offsets (with the
+      // reflection of the fused caller entry) and validity are computed once per tile: 7 instead of 12
+      // coordinate computations, none inside the channel loop.
       float v[4][3][4];
+      int ro[4], co[3];
+      bool rok[4], cok[3];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         const int yy = tc.y0 - 1 + rr;
+        rok[rr] = (yy >= 0) && (yy < p.H);
+        ro[rr] = reflect_src(yy, sH) * sW;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x - 1 + dx;
+        cok[dx] = (xx >= 0) && (xx < p.W);
+        co[dx] = reflect_src(xx, sW);
+      }
+      // per-channel plane pointers of this frame (channel in_c.. = noise map, or a constant fill)
+      const float* pc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        pc[c] = (c < in_c) ? in + (static_cast<long long>(tc.t) * in_c + c) * plane
+                           : (nmap && c == in_c ? nmap + static_cast<long long>(tc.t) * plane : nullptr);
+      const float fill = p.use_sigma ? p.sigma_const : 0.f;      // constant noise map (inside the image)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const int xx = x - 1 + dx;
-          const bool ok = (yy >= 0) && (yy < p.H) && (xx >= 0) && (xx < p.W);
-          const long long o = static_cast<long long>(reflect_src(yy, sH)) * sW + reflect_src(xx, sW);
+          const bool ok = rok[rr] && cok[dx];
+          const int o = ro[rr] + co[dx];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float f = 0.f;
-            if (ok) {
-              if (c < in_c) f = __ldg(in + (static_cast<long long>(tc.t) * in_c + c) * plane + o);
-              else if (nmap) f = __ldg(nmap + static_cast<long long>(tc.t) * plane + o);
-              else if (p.use_sigma) f = p.sigma_const;
-            }
+            if (ok) f = pc[c] ? __ldg(pc[c] + o) : (c == in_c ? fill : 0.f);
             v[rr][dx][c] = f;
           }
         }
