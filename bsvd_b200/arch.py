@@ -270,6 +270,22 @@ class BSVD(nn.Module):
                 Fr, H, W, torch.cuda.current_stream(dev).cuda_stream))
         return out
 
+    def denoise_frames_u8(self, frames, sigma, bgr=False):
+        """Decoded frames in, displayable frames out: uint8 [F,H,W,3] (HWC; bgr=True for cv2's channel
+        order) -> uint8 [F,H,W,3].  /255 normalisation (img2tensor) happens in the first kernel's
+        loads, clamp + *255 + round (tensor2img) in the last kernel's stores (bsvd_denoise_clip_u8)."""
+        dev = frames.device if frames.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            lib = self._ensure_handle(dev)
+            x = frames.detach().to(dev).contiguous()
+            assert x.dtype == torch.uint8 and x.dim() == 4 and x.shape[-1] == 3
+            Fr, H, W, _ = x.shape
+            out = torch.empty_like(x)
+            capi.check(lib.bsvd_denoise_clip_u8(
+                self._handle, x.data_ptr(), -1.0 if sigma is None else float(sigma), out.data_ptr(),
+                Fr, H, W, 1 if bgr else 0, torch.cuda.current_stream(dev).cuda_stream))
+        return out
+
     def denoise_host(self, input_host, noise_map_host=None, out_host=None):
         """End-to-end entry with HOST buffers (pinned recommended): H2D + forward + D2H inside the
         C ABI (bsvd_forward_clip_host).  input_host: fp32 [T,C,H,W] CPU tensor -> fp32 [T,3,H,W]."""

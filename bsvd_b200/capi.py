@@ -26,6 +26,7 @@ EXPORTS = (
     "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
     "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info", "bsvd_last_stage_ms",
     "bsvd_forward_clip_host_async", "bsvd_host_sync", "bsvd_denoise_clip", "bsvd_psnr",
+    "bsvd_denoise_clip_u8",
 )
 NUM_STAGES = 33
 
@@ -73,6 +74,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_host_sync.argtypes = [vp]
     lib.bsvd_denoise_clip.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, vp]
     lib.bsvd_psnr.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
+    lib.bsvd_denoise_clip_u8.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, ci, vp]
     lib.bsvd_stream_push.argtypes = [vp, vp, vp, vp, ci, ci, ci, cip, vp]
     lib.bsvd_reset.argtypes = [vp]
     lib.bsvd_last_launch_count.argtypes = [vp]

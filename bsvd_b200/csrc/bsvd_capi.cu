@@ -335,6 +335,8 @@ struct StageLaunch {
   const float* first_in = nullptr;
   const float* first_nmap = nullptr;
   int first_inc = 4;
+  int first_u8 = 0;               // raw input is uint8 HWC (bsvd_denoise_clip_u8)
+  float* first_norm = nullptr;    // fp32 [T][3][H][W] copy of the normalised frames (temp1 residual)
 };
 
 // pick the compile-time pipeline shape (conv_tc.cuh PIPE) the plan asks for
@@ -630,6 +632,8 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   if (!attr_done[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
     CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
     attr_done[dev & 63] = true;
   }
   if (!L.first_in) return fail("first stage launched without an input pointer");
@@ -641,10 +645,16 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (L.p.flags & EPI_BF16)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p));
+  float* no_norm = nullptr;
+  if (L.first_u8) {
+    if (L.p.flags & EPI_BF16)
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true, true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, L.first_norm));
+    else
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false, true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, L.first_norm));
+  } else if (L.p.flags & EPI_BF16)
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true, false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, no_norm));
   else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false, false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, no_norm));
   return 0;
 }
 
@@ -738,6 +748,9 @@ struct bsvd_handle {
   // raw-image view for the fused caller entry (0 / off for plain bsvd_forward_clip)
   int src_H = 0, src_W = 0, use_sigma = 0, clamp01 = 0;
   float sigma_const = 0.f;
+  int u8_io = 0, u8_bgr = 0;          // uint8 HWC frames in and out (bsvd_denoise_clip_u8)
+  float* d_norm = nullptr;            // normalised fp32 planes of the uint8 input (temp1 residual)
+  size_t d_norm_bytes = 0;
   // per-stage event timing
   int profiling = 0;
   std::vector<std::vector<cudaEvent_t>> ev_sets;   // each: BSVD_NUM_STAGES + 1 events
@@ -956,6 +969,7 @@ int bsvd_destroy(bsvd_handle* h) {
   }
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  if (h->d_norm) cudaFree(h->d_norm);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_nmap) cudaFree(h->d_nmap);
   if (h->d_out) cudaFree(h->d_out);
@@ -1041,16 +1055,18 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   }
   // stage 0 (input staging) is fused into temp1.inc.convblock.0 (first_conv.cuh)
   h->plan[0].first_in = in; h->plan[0].first_nmap = noise_map; h->plan[0].first_inc = in_c;
+  h->plan[0].first_u8 = h->u8_io; h->plan[0].first_norm = h->u8_io ? h->d_norm : nullptr;
   if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   int launches = 0;
-  h->plan[15].p.resid_in = in;          // temp1 residual reads the raw input (skip1)
-  h->plan[15].p.resid_C = in_c;
+  h->plan[15].p.resid_in = h->u8_io ? h->d_norm : in;   // temp1 residual reads the raw input (skip1)
+  h->plan[15].p.resid_C = h->u8_io ? 3 : in_c;
   h->plan[BSVD_NUM_LAYERS - 1].p.out = out;
   // raw-image view of the first / residual / last kernels (bsvd_denoise_clip sets h->src_*)
   for (int l : {0, 15, BSVD_NUM_LAYERS - 1}) {
     ConvParams& q = h->plan[l].p;
     q.src_H = h->src_H; q.src_W = h->src_W;
     q.use_sigma = h->use_sigma; q.sigma_const = h->sigma_const; q.clamp01 = h->clamp01;
+    q.u8_bgr = h->u8_bgr; q.out_u8 = h->u8_io;
   }
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
     if (launch_stage(h->plan[l], st)) return 1;
@@ -1074,6 +1090,23 @@ int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, 
   // a 3-channel raw input: the 4th (noise-map) slot is synthesised by the first kernel
   const int rc = bsvd_forward_clip(h, in, nullptr, out, T, 3, Hp, Wp, stream);
   h->src_H = h->src_W = 0; h->use_sigma = 0; h->clamp01 = 0;
+  return rc;
+}
+
+int bsvd_denoise_clip_u8(bsvd_handle* h, const uint8_t* in, float sigma, uint8_t* out, int T, int H,
+                         int W, int bgr, void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  const size_t need = (size_t)T * 3 * H * W * sizeof(float);
+  if (h->d_norm_bytes < need) {
+    if (h->d_norm) cudaFree(h->d_norm);
+    h->d_norm = nullptr; h->d_norm_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_norm, need));
+    h->d_norm_bytes = need;
+  }
+  h->u8_io = 1; h->u8_bgr = bgr ? 1 : 0;
+  const int rc = bsvd_denoise_clip(h, reinterpret_cast<const float*>(in), sigma,
+                                   reinterpret_cast<float*>(out), T, H, W, stream);
+  h->u8_io = 0; h->u8_bgr = 0;
   return rc;
 }
 

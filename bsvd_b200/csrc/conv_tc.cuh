@@ -116,6 +116,8 @@ struct ConvParams {
   int use_sigma;        // 1: the 4th input channel is the constant sigma_const (no noise-map tensor)
   float sigma_const;
   int clamp01;
+  int u8_bgr;           // uint8 HWC frame I/O (bsvd_denoise_clip_u8): 1 = channel order B,G,R
+  int out_u8;           // last kernel: store round(clamp(x) * 255) as uint8 [T][H][W][3] (tensor2img)
 };
 // reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
 __device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }

@@ -163,13 +163,18 @@ final_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(tc.t) * 3 * plane +
                      static_cast<long long>(y) * sW + x;
           if (y < sH && x < sW) {
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) +
+                          (static_cast<long long>(tc.t) * plane + static_cast<long long>(y) * sW + x) * 3;
 #pragma unroll
             for (int co = 0; co < 3; ++co) {
               const float conv = __uint_as_float(d[i][0][co]) + __uint_as_float(d[i][1][co]) +
                                  __uint_as_float(d[i][2][co]) + bias_s[co];
               float r = sv[co] - conv;
               if (p.clamp01) r = fminf(fmaxf(r, 0.f), 1.f);      // temp_denoise: torch.clamp(out, 0, 1)
-              o[co * plane] = r;
+              if (p.out_u8)      // tensor2img (img_util.py): (img * 255.0).round() as uint8, HWC
+                o8[p.u8_bgr ? 2 - co : co] = static_cast<uint8_t>(__float2uint_rn(r * 255.0f));
+              else
+                o[co * plane] = r;
             }
           }
         }

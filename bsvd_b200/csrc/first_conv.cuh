@@ -23,10 +23,15 @@ constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
 // epilogue staging: two 2 KB tiles per warp (units leave through TMA stores, see conv_tc.cuh)
 constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * 2 * kStageBytesPerWarp;
 
-template <bool BF16>
+// U8: the raw input is uint8 [T][H][W][3] (decoded frames, HWC; ConvParams::u8_bgr = channel order
+// B,G,R as cv2 delivers them): normalised with /255 on the fly (img2tensor,
+// BasicSR/basicsr/utils/img_util.py), and the normalised RGB planes of every pixel are also written
+// to `norm_out` (fp32 [T][3][H][W]) for the temp1 residual, which needs the raw input again.
+template <bool BF16, bool U8 = false>
 __global__ void __launch_bounds__(kFirstThreads, 1)
 first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, int in_c,
-                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p) {
+                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p,
+                  float* __restrict__ norm_out = nullptr) {
   constexpr int NT = 64;
   constexpr int kAccCols = kFirstR * NT;
   constexpr int kTmemCols = 2 * kAccCols;
@@ -119,11 +124,35 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         for (int dx = 0; dx < 3; ++dx) {
           const bool ok = rok[rr] && cok[dx];
           const int o = ro[rr] + co[dx];
+          if constexpr (U8) {
+            const uint8_t* px = reinterpret_cast<const uint8_t*>(in) +
+                                (static_cast<long long>(tc.t) * plane + o) * 3;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float f = 0.f;
-            if (ok) f = pc[c] ? __ldg(pc[c] + o) : (c == in_c ? fill : 0.f);
-            v[rr][dx][c] = f;
+            for (int c = 0; c < 3; ++c)
+              v[rr][dx][c] = ok ? static_cast<float>(__ldg(px + (p.u8_bgr ? 2 - c : c))) / 255.0f : 0.f;
+            v[rr][dx][3] = (ok && in_c == 3) ? fill : 0.f;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float f = 0.f;
+              if (ok) f = pc[c] ? __ldg(pc[c] + o) : (c == in_c ? fill : 0.f);
+              v[rr][dx][c] = f;
+            }
+          }
+        }
+      }
+      if constexpr (U8) {
+        // this thread's own two pixels (rows y0, y0+1 at column x): normalised RGB for the residual
+        if (norm_out && x < sW) {
+#pragma unroll
+          for (int r = 0; r < kFirstR; ++r) {
+            const int y = tc.y0 + r;
+            if (y < sH) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                norm_out[(static_cast<long long>(tc.t) * 3 + c) * plane + static_cast<long long>(y) * sW + x] =
+                    v[r + 1][1][c];
+            }
           }
         }
       }

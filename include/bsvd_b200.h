@@ -97,6 +97,16 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
 int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
                       void* stream);
 
+/* -- frame I/O ----------------------------------------------------------------------
+ * The same call on decoded frames: in/out are device uint8 [T, H, W, 3] (HWC, bgr != 0: channel
+ * order B,G,R as cv2.imread delivers it).  The first kernel normalises with /255 while it builds
+ * its patches (img2tensor, BasicSR/basicsr/utils/img_util.py; ValFolderDataset,
+ * Experimental_root/data/video_dali_dataset.py:199-249), the last kernel stores
+ * round(clamp(x, 0, 1) * 255) (tensor2img, DenoisingModel save path denoising_model.py:276-310):
+ * bit-identical to uint8 -> float -> bsvd_denoise_clip -> uint8 done with separate passes. */
+int bsvd_denoise_clip_u8(bsvd_handle* h, const uint8_t* in, float sigma, uint8_t* out, int T, int H,
+                         int W, int bgr, void* stream);
+
 /* -- on-device PSNR ----------------------------------------------------------------
  * replaces calculate_psnr_float (BasicSR/basicsr/metrics/psnr_ssim.py:130-168) applied per frame:
  * a, b: device fp32 [T, C, H, W] in [0,1]; crop_border pixels are ignored on every edge;

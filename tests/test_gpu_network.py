@@ -310,6 +310,29 @@ def test_fused_denoise_entry_is_bit_identical_to_the_unfused_steps(hw):
     assert torch.equal(net(x4[None])[0], y1)
 
 
+@pytest.mark.parametrize("bgr", [False, True])
+def test_uint8_frame_io_is_bit_identical_to_separate_passes(bgr):
+    """bsvd_denoise_clip_u8: uint8 HWC frames -> /255 (img2tensor) -> denoise -> clamp, *255, round
+    (tensor2img) -> uint8 HWC, all inside the first / last kernels == the same with torch passes."""
+    net, _ = make_net()
+    g = torch.Generator().manual_seed(9)
+    frames = torch.randint(0, 256, (3, 30, 46, 3), generator=g, dtype=torch.uint8).cuda()
+    sigma = 25.0 / 255.0
+    got = net.denoise_frames_u8(frames, sigma, bgr=bgr)
+    # img2tensor normalises on the host with numpy: a true fp32 division (torch's CUDA kernel would
+    # multiply by the rounded reciprocal, which differs in the last place)
+    chw = torch.from_numpy(frames.cpu().numpy().astype(np.float32) / np.float32(255.0)).permute(0, 3, 1, 2)
+    if bgr:
+        chw = chw.flip(1)
+    den = net.denoise_sequence(chw.contiguous().cuda(), sigma)
+    ref = (den * 255.0).round().to(torch.uint8)
+    if bgr:
+        ref = ref.flip(1)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    assert got.dtype == torch.uint8 and got.shape == frames.shape
+    assert torch.equal(got, ref)
+
+
 def test_psnr_on_device_matches_calculate_psnr_float():
     """bsvd_psnr == calculate_psnr_float (psnr_ssim.py:130-168) per frame: CHW float [0,1],
     crop_border, -10 log10(mse), inf when identical."""
