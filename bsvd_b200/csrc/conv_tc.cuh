@@ -1,12 +1,13 @@
 // conv_tc.cuh — fused 3x3 convolution stage on sm_100a tensor cores (tcgen05 + TMEM + TMA).
 //
-// One kernel family covers every conv of BSVD-64 (reference: nn.Conv2d call sites
+// One kernel family covers every conv of the BSVD DenBlocks (reference: nn.Conv2d call sites
 // bsvd_arch.py:31-38, 208-213, 238-239, 265, 295-298) together with what the reference runs as
-// separate elementwise kernels around it: bias, ReLU6 (:185-192), PixelShuffle (:266), the skip
-// add (:402-406), the residual (:408-414) and the bidirectional-buffer channel shift (:42-50).
+// separate elementwise kernels around it: bias, ReLU6 / ReLU (:185-192), PixelShuffle (:266), the
+// skip add (:402-406), the residual (:408-414) and the bidirectional-buffer channel shift (:42-50).
 //
 // Formulation: implicit GEMM, im2col-free.
-//   M = 128 consecutive output pixels of one image row (one tcgen05.mma, cta_group::1, M=128)
+//   M = 128 consecutive output pixels of one image row per CTA; CTA pairs (cta_group::2) issue one
+//       M=256 tcgen05.mma over two pixel tiles and share each filter slab (half per CTA)
 //   N = NTILE output channels
 //   K = 9 taps x Cin, walked as (64-channel chunk) x (tap) x (4 k-steps of 16)
 // Activations live in HBM as NHWC 16-bit, so a pixel's 64-channel chunk is one 128-byte row of
@@ -14,15 +15,19 @@
 // [(R+2) rows][130 px][64 ch] per chunk with a single TMA box (out-of-bounds = conv zero padding)
 // and form the nine shifted A operands purely by offsetting the UMMA descriptor start address by
 // (dy*130+dx)*128 bytes — no im2col, no re-load.  Stride-2 convs load one box per tap from a 5-D
-// space-to-depth view of the same NHWC tensor.  Weights are pre-swizzled on the host and
-// streamed with 1-D bulk copies (or kept resident when the whole filter bank fits).
+// space-to-depth view of the same NHWC tensor.  Weights are pre-swizzled on the host and streamed
+// through a ring of filter slabs (or kept resident when the whole bank fits: the 64->64 stages,
+// which also stack the vertical taps in N, see the PIPE == 2 branch of the MMA warp).
 //
 // Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0      TMA producer          warp 1      MMA issuer + TMEM allocator
+//   warp 0      TMA producer          warp 1      MMA issuer + TMEM allocator (leader CTA issues)
 //   warps 2..9  epilogue: TMEM -> registers -> bias/act/skip/residual in fp32 -> 16-bit ->
-//               per-warp swizzled smem staging -> coalesced 128-bit global stores (the
-//               bidirectional-buffer fold routing and PixelShuffle scatter happen at the store)
+//               per-warp staging tile in SWIZZLE_64B layout -> TMA store of the unit, or (stages
+//               whose output carries the temporal shift) transposed read-back and 128-bit global
+//               stores routed to frame t-1 / t / t+1
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
+// PixelShuffle + skip stages accumulate the skip tensor on the tensor core (identity MMA on
+// TMA-loaded skip blocks, ConvParams::skip_mma) instead of adding it in the epilogue.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>

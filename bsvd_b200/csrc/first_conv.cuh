@@ -3,7 +3,7 @@
 // Reference: the torch.cat([input, noise_map]) of BSVD.forward (bsvd_arch.py:492-493) and the first
 // nn.Conv2d of InputCvBlock (bsvd_arch.py:207-209).  With only 4 input channels the 3x3x4 patch of a
 // pixel (36 values) fits one 128-byte K row, so the conv is a single-tap GEMM with K = 64 (36 used).
-// Instead of materialising the patches in HBM (a 663 MB round trip per 10-frame clip) four producer
+// Instead of materialising the patches in HBM (a 663 MB round trip per 10-frame clip) eight producer
 // warps build them directly in shared memory, in the SWIZZLE_128B K-major layout tcgen05.mma reads:
 //   warps 0-7  patch producers, two groups of 4 warps taking alternate tiles: fp32 NCHW (+ noise
 //              map) -> 16-bit swizzled rows, fence.proxy.async
