@@ -154,6 +154,42 @@ def u8(args):
         "checksum": int(out_h.long().sum())}), flush=True)
 
 
+def torch_gpu(args):
+    """Like-for-like bar: the reference's own formulation — one F.conv2d / pixel_shuffle /
+    cat per op through PyTorch + cuDNN (the oracle restatement makes exactly the calls the reference's
+    TSN/BSVD classes make) — on the SAME B200, for fp32 (TF32 off / on) and fp16 tensors."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    T, H, W = args.frames, 540, 960
+    sd = O.make_synthetic_params(0, 0.5)
+    x, _ = O.make_synthetic_clip(T, H, W, seed=1)
+    for name, dt, tf32 in (("fp32, TF32 off", torch.float32, False), ("fp32, TF32 on (PyTorch default for convs)", torch.float32, True),
+                           ("fp16 weights and activations (profile.py mode)", torch.float16, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        layers = [(w.to(dev, dt), b.to(dev, dt)) for w, b in O.layers_from_tsn_state(sd)]
+        xd = x.to(dev, dt)
+        with torch.no_grad():
+            for _ in range(2):
+                y = O.forward_clip(layers, xd)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                y = O.forward_clip(layers, xd)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        print(json.dumps({
+            "metric": "denoised frames/sec at 540x960 (c=64)", "value": T / ms * 1e3, "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "impl": "PyTorch + cuDNN, op by op (reference formulation)",
+            "dtype": name, "config": {"workload": f"BSVD-64 forward, 1 clip [1,{T},4,{H},{W}], clip order"},
+            "checksum": float(y.float().abs().sum())}), flush=True)
+        del layers, xd, y
+        torch.cuda.empty_cache()
+
+
 def tiles(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,7 +246,7 @@ def tiles(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["stream", "tiles", "c32", "u8"])
+    ap.add_argument("mode", choices=["stream", "tiles", "c32", "u8", "torch"])
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--precision", default=None)
@@ -220,7 +256,10 @@ if __name__ == "__main__":
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
-    if a.mode == "u8":
+    if a.mode == "torch":
+        a.frames = a.frames or 10
+        torch_gpu(a)
+    elif a.mode == "u8":
         a.frames = a.frames or 10
         a.precision = a.precision or "fp16"
         u8(a)
