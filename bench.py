@@ -173,7 +173,7 @@ def run_b200(args):
                act='relu6', pretrain_ckpt=None, precision=prec)
     net.load_tsn_state(sd)
     net = net.to(dev).eval()
-    x_host, _ = O.make_synthetic_clip(T_CLIP, H, W, seed=1 + rank)
+    x_host, clean_host = O.make_synthetic_clip(T_CLIP, H, W, seed=1 + rank)
     x_host = x_host.pin_memory()
     x_dev = x_host.to(dev)
     gathered = None
@@ -323,8 +323,12 @@ def run_b200(args):
     with torch.no_grad():
         ys = net(xs[None].to(dev))[0].float().cpu()
     ref = O2.forward_clip(layers, xs)
+    # PSNR delta vs the reference (calculate_psnr_float semantics: clamp to [0,1], crop_border 2)
+    dpsnr = [O2.psnr_float(ys[i].clamp(0, 1), clean_host[i]) - O2.psnr_float(ref[i].clamp(0, 1), clean_host[i])
+             for i in range(ys.shape[0])]
     parity = {"max_abs": float((ys - ref).abs().max()), "mean_abs": float((ys - ref).abs().mean()),
               "tolerance": 1e-3 if prec != "bf16" else 1e-2,
+              "psnr_delta_db": {"mean": float(sum(dpsnr) / len(dpsnr)), "worst": float(min(dpsnr))},
               "sample": f"[1,2,4,{H},{W}] vs fp32 CPU oracle"}
 
     cpu = None
