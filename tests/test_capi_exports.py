@@ -115,3 +115,24 @@ def test_module_forward_fails_loudly_without_gpu():
     net = _net()
     with pytest.raises(Exception):
         net(torch.zeros(1, 2, 4, 8, 8))
+
+
+def test_header_is_valid_c_and_a_plain_c_client_links(tmp_path):
+    """include/bsvd_b200.h compiles as C99 and examples/c_client.c links against the library with
+    nothing but gcc (no torch, no CUDA headers); without a GPU the client reports the loud failure."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.join(ROOT, "bsvd_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_client.c"), "-L" + libdir, "-lbsvd_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "sm_100a" in out.stdout
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in out.stdout
+    else:
+        assert "layer 31: weight [3,64,3,3]" in out.stdout
