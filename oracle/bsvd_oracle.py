@@ -280,8 +280,9 @@ class _BiBuffer:
 class _StreamDenBlock:
     """DenBlock.forward with None propagation and MemSkip FIFOs (bsvd_arch.py:308-322, 374-414)."""
 
-    def __init__(self, layers):
+    def __init__(self, layers, act: str = "relu6"):
         self.l = layers
+        self.act = _act_fn(act)
         self.bib = {i: _BiBuffer(*layers[i]) for i in SHIFT_LAYERS}
         self.skip1, self.skip2, self.skip3 = [], [], []
 
@@ -292,13 +293,14 @@ class _StreamDenBlock:
     def _mem(self, i, x):   # MemCvBlock :133-142
         x = self.bib[i](x)
         if x is not None:
-            x = _relu6(x)
+            x = self.act(x)
         x = self.bib[i + 1](x)
         if x is not None:
-            x = _relu6(x)
+            x = self.act(x)
         return x
 
     def __call__(self, in1):
+        _relu6 = self.act  # noqa: F811  (the block's activation)
         conv = lambda i, t, s=1: F.conv2d(t, self.l[i][0], self.l[i][1], stride=s, padding=1)  # noqa: E731
         if in1 is not None:
             self.skip1.insert(0, in1[:, 0:3])
@@ -331,9 +333,9 @@ class StreamOracle:
 
     shift_num = 16   # count_shift(), bsvd_arch.py:554-560
 
-    def __init__(self, layers):
-        self.t1 = _StreamDenBlock(layers[:16])
-        self.t2 = _StreamDenBlock(layers[16:])
+    def __init__(self, layers, act: str = "relu6"):
+        self.t1 = _StreamDenBlock(layers[:16], act)
+        self.t2 = _StreamDenBlock(layers[16:], act)
 
     def reset(self):
         self.t1.reset()

@@ -73,6 +73,23 @@ def test_c32_blind_clip_matches_reference(path):
     assert float((y - torch.from_numpy(g["y_clip"])).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("T,H,W", [(1, 8, 12), (4, 12, 8), (7, 8, 8)])
+def test_c32_stream_order_equals_clip_order(T, H, W):
+    """The oracle's two schedules agree for the c32 / 'relu' configuration too (the reference's
+    streaming class cannot run blind models with mid_ch != 3, so this leg has no reference fixture;
+    the non-blind variant uses the same code with a 4-channel first conv)."""
+    c = O.C32
+    for in_ch in (3, 4):
+        sd = O.make_synthetic_params(11, 0.5, in_ch=in_ch, chns=c["chns"], mid_ch=c["mid_ch"],
+                                     interm_ch=c["interm_ch"])
+        layers = O.layers_from_tsn_state(sd)
+        x, _ = O.make_synthetic_clip(T, H, W, 12)
+        x = x[:, :in_ch].contiguous()
+        y_clip = O.forward_clip(layers, x, act=c["act"])
+        y_stream = O.StreamOracle(layers, act=c["act"]).streaming_forward(x)
+        assert float((y_clip - y_stream).abs().max()) <= 1e-4
+
+
 def test_param_count_and_keys():
     sd = O.make_synthetic_params(0)
     assert sum(v.numel() for v in sd.values()) == 9815683   # SURVEY §0 [probe]
