@@ -1,0 +1,140 @@
+// stage_launch.cuh — launch record of one fused conv stage and the dispatch from a plan's run-time
+// description (tile shape, operand type, epilogue feature set, pipeline shape) to the matching
+// conv3x3_tc_kernel instance.  Shared by bsvd_capi.cu (host schedules) and conv_inst.cu (the
+// translation units that instantiate the kernels, one per (NTILE, R) pair so they build in parallel).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "conv_tc.cuh"
+
+namespace bsvd {
+
+// defined in bsvd_capi.cu: records the message bsvd_last_error() returns, yields 1
+int fail(const char* fmt, ...);
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// dynamic shared memory: 227 KB opt-in limit minus the kernel's static shared (barriers, bias)
+constexpr size_t kSmemOptIn = 232448 - 3072;
+
+struct StageLaunch;
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
+static int launch_inst(const StageLaunch& L, cudaStream_t st);
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
+static int launch_pipe(const StageLaunch& L, cudaStream_t st);
+struct StageLaunch {
+  CUtensorMap map;      // activations
+  CUtensorMap map_w;    // packed weights (CTA-pair kernels)
+  CUtensorMap map_s;    // skip tensor, PixelShuffle view (skip add on the tensor core)
+  CUtensorMap map_o;    // output tensor (TMA stores)
+  ConvParams p;
+  int grid = 0;
+  size_t smem = 0;
+  int ntile = 0, rows = 0;
+  int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
+  int ew = 8;           // epilogue warps (8 or 16)
+  // fused first stage (first_conv.cuh): raw network input, patched per call
+  const float* first_in = nullptr;
+  const float* first_nmap = nullptr;
+  int first_inc = 4;
+  int first_u8 = 0;               // raw input is uint8 HWC (bsvd_denoise_clip_u8)
+  float* first_norm = nullptr;    // fp32 [T][3][H][W] copy of the normalised frames (temp1 residual)
+};
+
+// pick the compile-time pipeline shape (conv_tc.cuh PIPE) the plan asks for
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
+static int launch_inst(const StageLaunch& L, cudaStream_t st) {
+  if constexpr (CTA2) {
+    const int mode = L.p.mode, res = L.p.w_resident;
+    if (L.p.desc_variant != 0 || L.p.tap_begin != 0 || L.p.tap_end != (mode == 2 ? 3 : 9)) {
+      // debug switches / partial tap ranges only exist in the generic pipeline
+    } else if constexpr (NTILE == 64 && R == 2) {
+      if (mode == 2 && res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 2>(L, st);
+    } else {
+      if (mode == 0 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 0>(L, st);
+      if constexpr ((MASK & (EPI_PIXSHUF | EPI_RESID_IN)) == 0)
+        if (mode == 1 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 1>(L, st);
+    }
+  }
+  return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 3>(L, st);
+}
+template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
+static int launch_pipe(const StageLaunch& L, cudaStream_t st) {
+  static bool attr_done[64] = {};      // per device: the attribute is per (function, device)
+  auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK, EW, PIPE>;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+    attr_done[dev & 63] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(64 + 32 * EW);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL, see conv_tc.cuh
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (CTA2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, L.map, L.map_w, L.map_s, L.map_o, L.p));
+  return 0;
+}
+// Epilogue feature sets the kernels are specialised for; a stage runs on the smallest set that
+// covers its flags (the single-CTA debug path only has the general instance).
+constexpr int kMaskAct = EPI_RELU6 | EPI_RELU;       // the activation is a run-time flag inside every instance
+constexpr int kMaskPlain = kMaskAct;
+constexpr int kMaskShift = kMaskAct | EPI_SHIFT;
+constexpr int kMaskResid = kMaskAct | EPI_RESID_IN;
+// PixelShuffle stages: the skip add runs on the tensor core (ConvParams::skip_mma), so the
+// epilogue instances carry no skip path
+constexpr int kMaskUpTma = EPI_PIXSHUF | EPI_TMA_OUT;   // upc1.convblock.0: units leave through TMA stores
+constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0 with the skip on the tensor core (opt-in)
+constexpr int kMaskUpSkipShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0: skip added in the epilogue
+constexpr int kMaskAll = kMaskAct | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
+template <int NTILE, int R, bool BF16>
+static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
+  if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
+  const int f = L.p.flags & kMaskAll;
+  {
+    if (L.p.tma_out) {     // no temporal shift on the output: units leave through TMA stores
+      if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain | EPI_TMA_OUT, 8>(L, st);
+      if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid | EPI_TMA_OUT, 8>(L, st);
+      if constexpr (NTILE != 64)
+        if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift | EPI_TMA_OUT, 8>(L, st);
+    }
+    if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
+    if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
+    if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
+    if constexpr (NTILE == 256 && R == 1) {
+      if (L.p.tma_out && (f & ~kMaskUpTma) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpTma, 8>(L, st);
+      if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpShift, 8>(L, st);
+      if ((f & ~kMaskUpSkipShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpSkipShift, 8>(L, st);
+    }
+  }
+  return launch_inst<NTILE, R, BF16, true, kMaskAll, 8>(L, st);
+}
+// external linkage: explicitly instantiated in conv_inst.cu, declared `extern template` by callers
+template <int NTILE, int R>
+int launch_one(const StageLaunch& L, cudaStream_t st) {
+  return (L.p.flags & EPI_BF16) ? launch_dtype<NTILE, R, true>(L, st)
+                                : launch_dtype<NTILE, R, false>(L, st);
+}
+
+
+}  // namespace bsvd
