@@ -60,6 +60,14 @@ def _attach(root: nn.Module, dotted: str, leaf: nn.Module) -> None:
 
 
 def _layer_shapes(block, chns, mid_ch, in_ch, out_ch, interm_ch):
+    """(out_ch, in_ch, stride) of the 16 convs of DenBlock `block`.
+
+    blind=True: only temp1 drops the noise-map channel (in_ch 4 -> 3); temp2 always reads temp1's mid_ch
+    channels.  This is the TSN/WNet training model's layout (wnet_models.py:233-278, the class the
+    published blind checkpoints were trained with).  The reference's streaming class passes `blind` to
+    BOTH DenBlocks (bsvd_arch.py:451-452), which makes its temp2.inc.convblock.0 a Conv2d(3, interm) and
+    lets it run only when mid_ch == 3; for mid_ch == 3 the two layouts coincide, for any other mid_ch the
+    reference class cannot execute, so state_dict() shapes follow the TSN layout here."""
     c0, c1, c2 = chns
     cin = in_ch if block == 0 else mid_ch
     cout = mid_ch if block == 0 else out_ch
@@ -70,6 +78,10 @@ def _layer_shapes(block, chns, mid_ch, in_ch, out_ch, interm_ch):
 
 class BSVD(nn.Module):
     """Bidirectional-buffer streaming video denoiser, B200-native (see module docstring)."""
+
+    # process-wide counters (the plugin prints them when it ran a reference script, so a harness can
+    # tell that ARCH_REGISTRY['BSVD'] really resolved to this class and that its kernels ran)
+    stats = {"instances": 0, "forward_calls": 0, "kernel_launches": 0}
 
     def __init__(self, chns=[32, 64, 128], mid_ch=3, shift_input=False, in_ch=4, out_ch=3,
                  norm='bn', act='relu', interm_ch=30, blind=False,
@@ -103,9 +115,11 @@ class BSVD(nn.Module):
         self.precision = precision or os.environ.get("BSVD_B200_PRECISION")  # 'fp16' | 'bf16' | None
         self._handle = None
         self._handle_prec = None
+        self._handle_dev = None
         self._weights_sig = None
         self._stream_out = None
         self.reset_params()
+        BSVD.stats["instances"] += 1
         if pretrain_ckpt is not None:
             self.load(pretrain_ckpt)
 
@@ -169,7 +183,10 @@ class BSVD(nn.Module):
         if not torch.cuda.is_available():
             raise capi.BsvdError("bsvd_b200 needs a CUDA device (B200, sm_100a); no CPU fallback")
         prec = self._select_precision()
-        if self._handle is not None and self._handle_prec != prec:
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        # a native handle (packed weights, workspaces, tensor maps) is bound to ONE device: after
+        # net.to('cuda:1'), or for an input on another GPU, it is rebuilt there
+        if self._handle is not None and (self._handle_prec != prec or self._handle_dev != dev_index):
             self._destroy()
         if self._handle is None:
             cfg = capi.BsvdConfig()
@@ -178,10 +195,10 @@ class BSVD(nn.Module):
             cfg.in_ch, cfg.out_ch = self.cfg["in_ch"], self.cfg["out_ch"]
             cfg.act_relu6, cfg.norm_none = (1 if self.cfg["act"] == "relu6" else 0), 1
             cfg.precision = capi.PREC_FP16 if prec == "fp16" else capi.PREC_BF16
-            cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+            cfg.device = dev_index
             h = C.c_void_p()
             capi.check(lib.bsvd_create(C.byref(cfg), C.byref(h)))
-            self._handle, self._handle_prec, self._weights_sig = h, prec, None
+            self._handle, self._handle_prec, self._handle_dev, self._weights_sig = h, prec, dev_index, None
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if sig != self._weights_sig:
             for i, conv in enumerate(self._convs()):
@@ -192,10 +209,16 @@ class BSVD(nn.Module):
             self._weights_sig = sig
         return lib
 
+    def _module_device(self):
+        """Device of the parameters when they are on a GPU, else the current CUDA device."""
+        w = self.temp1.inc.convblock._modules['0'].weight
+        return w.device if w.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
     def _destroy(self):
         if getattr(self, "_handle", None) is not None:
             try:
-                capi.load_library().bsvd_destroy(self._handle)
+                with torch.cuda.device(self._handle_dev):
+                    capi.load_library().bsvd_destroy(self._handle)
             except Exception:  # noqa: BLE001
                 pass
             self.__dict__["_handle"] = None
@@ -227,6 +250,8 @@ class BSVD(nn.Module):
             capi.check(lib.bsvd_forward_clip(
                 self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
                 out.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+            BSVD.stats["forward_calls"] += 1
+            BSVD.stats["kernel_launches"] += lib.bsvd_last_launch_count(self._handle)
         od = self._out_dtype()
         return out if od == torch.float32 else out.to(od)
 
@@ -290,7 +315,8 @@ class BSVD(nn.Module):
         """End-to-end entry with HOST buffers (pinned recommended): H2D + forward + D2H inside the
         C ABI (bsvd_forward_clip_host).  input_host: fp32 [T,C,H,W] CPU tensor -> fp32 [T,3,H,W]."""
         assert not input_host.is_cuda and input_host.dtype == torch.float32
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = self._module_device()
+        torch.cuda.set_device(dev)
         lib = self._ensure_handle(dev)
         x = input_host.contiguous()
         T, Cc, H, W = x.shape
@@ -308,18 +334,46 @@ class BSVD(nn.Module):
         host_sync() before reading `out_host`.  Buffers must be pinned and stay alive."""
         assert not input_host.is_cuda and input_host.dtype == torch.float32
         assert input_host.is_contiguous() and out_host.is_contiguous()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = self._module_device()
+        torch.cuda.set_device(dev)
         lib = self._ensure_handle(dev)
         T, Cc, H, W = input_host.shape
         nm = noise_map_host
         capi.check(lib.bsvd_forward_clip_host_async(
             self._handle, input_host.data_ptr(), nm.data_ptr() if nm is not None else None,
             out_host.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+        self._last_host_shape = (T, 3, H, W)
         return out_host
+
+    def last_device_output(self):
+        """Device-side [T,3,H,W] fp32 result of the latest denoise_host_async call (a view of the C
+        ABI's staging buffer, bsvd_host_last_output): valid for work ordered behind that call on the
+        current stream, until the call after next overwrites it."""
+        p = C.c_void_p()
+        capi.check(capi.load_library().bsvd_host_last_output(self._handle, C.byref(p)))
+
+        class _Holder:
+            pass
+        hold = _Holder()
+        hold.__cuda_array_interface__ = {"shape": self._last_host_shape, "typestr": "<f4",
+                                         "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(hold, device=torch.device("cuda", self._handle_dev))
+
+    def overflowed(self, reset=True):
+        """True if, since the last reset, an fp16-stored activation that is not clamped by ReLU6 left the
+        fp16 range (inf/NaN) where the reference's fp32 tensors would not (bsvd_overflow_flag; waits for
+        the device).  Switch such a model to precision='bf16'."""
+        if self._handle is None:
+            return False
+        flag = C.c_int(0)
+        with torch.cuda.device(self._handle_dev):
+            capi.check(capi.load_library().bsvd_overflow_flag(self._handle, C.byref(flag), 1 if reset else 0))
+        return bool(flag.value)
 
     def host_sync(self):
         if self._handle is not None:
-            capi.check(capi.load_library().bsvd_host_sync(self._handle))
+            with torch.cuda.device(self._handle_dev):
+                capi.check(capi.load_library().bsvd_host_sync(self._handle))
 
     # ---------------------------------------------------------------- streaming mode
     def feedin_one_element(self, x, noise_map=None):
@@ -357,7 +411,7 @@ class BSVD(nn.Module):
     def reset(self):
         """Clear all streaming buffers (bsvd_arch.py:459-461)."""
         self._stream_shape = None
-        if self._handle is not None:
+        if getattr(self, "_handle", None) is not None:
             capi.check(capi.load_library().bsvd_reset(self._handle))
 
     def count_shift(self):

@@ -26,7 +26,10 @@ EXPORTS = (
     "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
     "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info", "bsvd_last_stage_ms",
     "bsvd_forward_clip_host_async", "bsvd_host_sync", "bsvd_denoise_clip", "bsvd_psnr",
-    "bsvd_denoise_clip_u8",
+    "bsvd_denoise_clip_u8", "bsvd_overflow_flag", "bsvd_host_last_output",
+    "bsvd_peer_create", "bsvd_peer_handle_bytes", "bsvd_peer_get_handle", "bsvd_peer_open",
+    "bsvd_peer_local_data", "bsvd_peer_put", "bsvd_peer_put2d", "bsvd_peer_put3d", "bsvd_peer_signal", "bsvd_peer_wait",
+    "bsvd_peer_read_flag", "bsvd_peer_destroy",
 )
 NUM_STAGES = 33
 
@@ -72,6 +75,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_forward_clip_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.bsvd_forward_clip_host_async.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.bsvd_host_sync.argtypes = [vp]
+    lib.bsvd_host_last_output.argtypes = [vp, C.POINTER(vp)]
     lib.bsvd_denoise_clip.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, vp]
     lib.bsvd_psnr.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.bsvd_denoise_clip_u8.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, ci, vp]
@@ -80,6 +84,20 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_last_launch_count.argtypes = [vp]
     lib.bsvd_workspace_bytes.argtypes = [vp]
     lib.bsvd_workspace_bytes.restype = C.c_size_t
+    lib.bsvd_overflow_flag.argtypes = [vp, cip, ci]
+    sz, cu = C.c_size_t, C.c_uint
+    lib.bsvd_peer_create.argtypes = [ci, ci, sz, ci, C.POINTER(vp)]
+    lib.bsvd_peer_get_handle.argtypes = [vp, vp]
+    lib.bsvd_peer_open.argtypes = [vp, vp]
+    lib.bsvd_peer_local_data.argtypes = [vp]
+    lib.bsvd_peer_local_data.restype = vp
+    lib.bsvd_peer_put.argtypes = [vp, ci, sz, vp, sz, vp]
+    lib.bsvd_peer_put2d.argtypes = [vp, ci, sz, sz, vp, sz, sz, sz, vp]
+    lib.bsvd_peer_put3d.argtypes = [vp, ci, sz, sz, sz, vp, sz, sz, sz, sz, sz, vp]
+    lib.bsvd_peer_signal.argtypes = [vp, ci, ci, cu, vp]
+    lib.bsvd_peer_wait.argtypes = [vp, ci, cu, vp]
+    lib.bsvd_peer_read_flag.argtypes = [vp, ci, C.POINTER(cu)]
+    lib.bsvd_peer_destroy.argtypes = [vp]
     lib.bsvd_set_profiling.argtypes = [vp, ci]
     lib.bsvd_get_stage_ms.argtypes = [vp, C.POINTER(C.c_float), ci, cip]
     lib.bsvd_stage_info.argtypes = [vp, ci, cip, cip, cip, cip, cip]

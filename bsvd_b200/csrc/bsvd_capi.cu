@@ -299,6 +299,7 @@ struct StageIO {
   const float* resid_in = nullptr;
   int resid_C = 0;
   void* aux_out = nullptr;
+  unsigned* overflow = nullptr;
   // streaming: `skip` / `out` are ring bases of skip_T / out_T slots (0 = plain [T] tensors)
   int skip_T = 0, out_T = 0;
   long long skip_T_stride = 0, out_T_stride = 0;   // bytes
@@ -371,6 +372,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;
+  p.overflow = io.overflow;
   p.cin_chunks = s.cin_chunks;
   p.n_tiles = s.n_tiles();
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
@@ -514,7 +516,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
 }
 
 static int launch_first(const StageLaunch& L, cudaStream_t st) {
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
@@ -549,7 +551,7 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
   if (L.ntile == -1) return launch_first(L, st);
   if (L.ntile == 16) {
-    static bool attr_done[64] = {};
+    static std::atomic<bool> attr_done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
@@ -633,10 +635,9 @@ struct bsvd_handle {
   uint16_t* bufS = nullptr;   // compact [T][H][W][4] copy of temp1's output channels 0..3 (skip1 of temp2)
   std::vector<StageLaunch> plan;
   int last_launches = 0;
-  // raw-image view for the fused caller entry (0 / off for plain bsvd_forward_clip)
-  int src_H = 0, src_W = 0, use_sigma = 0, clamp01 = 0;
-  float sigma_const = 0.f;
-  int u8_io = 0, u8_bgr = 0;          // uint8 HWC frames in and out (bsvd_denoise_clip_u8)
+  unsigned long long weights_epoch = 0;   // bumped by bsvd_set_weights (cached CUDA graphs are rebuilt)
+  int device = 0;                     // CUDA device the handle (weights, workspaces, tensor maps) lives on
+  unsigned* d_overflow = nullptr;     // sticky flag: a stored 16-bit activation was not finite
   float* d_norm = nullptr;            // normalised fp32 planes of the uint8 input (temp1 residual)
   size_t d_norm_bytes = 0;
   // per-stage event timing
@@ -671,6 +672,36 @@ struct bsvd_handle {
     StreamLayer layers[BSVD_NUM_LAYERS];
   } stream;
 };
+
+// Options of ONE call (the fused caller entries bsvd_denoise_clip / _u8 set them); they travel as an
+// argument so that no call-scoped state is ever parked on the handle.
+struct CallOpts {
+  int src_H = 0, src_W = 0;           // raw-image view of the first / residual / last kernels (0 = same)
+  int use_sigma = 0, clamp01 = 0;
+  float sigma_const = 0.f;
+  int u8_io = 0, u8_bgr = 0;          // uint8 HWC frames in and out
+};
+
+// Every entry point runs on the device the handle was created on (weights, workspaces and tensor maps
+// live there); a call made with another device current is an error, never a silent remote access.
+static int check_device(const bsvd_handle* h) {
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != h->device)
+    return fail("handle belongs to CUDA device %d but device %d is current (create one handle per "
+                "device; bsvd_b200.arch.BSVD does this when the module is moved)", h->device, dev);
+  return 0;
+}
+static int check_dev_ptr(const bsvd_handle* h, const void* p, const char* what) {
+  if (!p) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if ((a.type == cudaMemoryTypeDevice) && a.device != h->device)
+    return fail("%s lives on CUDA device %d, the handle on device %d", what, a.device, h->device);
+  if (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered)
+    return fail("%s is a host pointer; this entry point takes device memory", what);
+  return 0;
+}
 
 static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 static void build_specs(bsvd_handle* h) {
@@ -762,6 +793,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
       StageIO io;
       io.in = src; io.T = T; io.H = sh; io.W = sw; io.out = dst;
       io.skip = skip; io.skip_C = skip_C; io.skip_frame_stride = skip_fs;
+      io.overflow = h->d_overflow;
       if (blk == 0 && l == 15) { io.resid_in = in; io.resid_C = in_c; io.aux_out = h->bufS; }
       return plan_stage(h->stages[blk * 16 + l], io, h->bf16, 0, &h->plan[blk * 16 + l]);
     };
@@ -834,8 +866,14 @@ int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
   if (major != 10) return fail("device compute capability %d.x is not sm_100a (B200)", major);
   bsvd_handle* h = new bsvd_handle();
   h->cfg = *cfg;
+  h->device = dev;
   h->bf16 = (cfg->precision == BSVD_PREC_BF16);
   build_specs(h);
+  if (cudaMalloc((void**)&h->d_overflow, sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(h->d_overflow, 0, sizeof(unsigned)) != cudaSuccess) {
+    delete h;
+    return fail("cudaMalloc of the overflow flag failed");
+  }
   *out = h;
   return 0;
 }
@@ -858,6 +896,7 @@ int bsvd_destroy(bsvd_handle* h) {
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
   if (h->d_norm) cudaFree(h->d_norm);
+  if (h->d_overflow) cudaFree(h->d_overflow);
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_nmap) cudaFree(h->d_nmap);
   if (h->d_out) cudaFree(h->d_out);
@@ -882,7 +921,21 @@ int bsvd_set_weights(bsvd_handle* h, int layer, const float* w, const float* bia
   if (sd.spec.cout_l != out_ch || sd.spec.cin_l != in_ch)
     return fail("layer %d expects weight [%d,%d,3,3], got [%d,%d,3,3]", layer, sd.spec.cout_l,
                 sd.spec.cin_l, out_ch, in_ch);
-  return upload_stage(sd, w, bias, h->bf16);
+  if (check_device(h)) return 1;
+  // A forward enqueued earlier (on any stream) may still read the packed weights: every kernel loads
+  // them before griddepcontrol.wait.  Weight updates are rare, so simply drain the device first.
+  if (sd.loaded) CUDA_TRY(cudaDeviceSynchronize());
+  if (upload_stage(sd, w, bias, h->bf16)) return 1;
+  // The bias also travels in the kernel-parameter bank of every cached launch record (clip plan,
+  // streaming templates): refresh those copies, or a reload after a forward would pair new weights
+  // with old biases.
+  auto refresh = [&](StageLaunch& L) {
+    std::copy(sd.bias_h.begin(), sd.bias_h.end(), L.p.bias_c);
+  };
+  if (!h->plan.empty()) refresh(h->plan[layer]);
+  if (h->stream.ws) refresh(h->stream.layers[layer].tmpl);
+  ++h->weights_epoch;
+  return 0;
 }
 
 int bsvd_set_profiling(bsvd_handle* h, int on) {
@@ -921,12 +974,23 @@ int bsvd_stage_info(const bsvd_handle* h, int stage, int* cin, int* cout, int* s
 }
 
 int bsvd_last_launch_count(const bsvd_handle* h) { return h ? h->last_launches : 0; }
+
+int bsvd_overflow_flag(bsvd_handle* h, int* flag, int reset) {
+  if (!h || !flag) return fail("null argument");
+  if (check_device(h)) return 1;
+  unsigned v = 0;
+  CUDA_TRY(cudaMemcpy(&v, h->d_overflow, sizeof(v), cudaMemcpyDeviceToHost));   // waits for prior work
+  if (reset && v) CUDA_TRY(cudaMemset(h->d_overflow, 0, sizeof(v)));
+  *flag = v ? 1 : 0;
+  return 0;
+}
 size_t bsvd_workspace_bytes(const bsvd_handle* h) { return h ? h->ws_bytes : 0; }
 
-int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
-                      int in_c, int H, int W, void* stream) {
+static int forward_clip_impl(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
+                             int in_c, int H, int W, void* stream, const CallOpts& o) {
   if (!h || !in || !out) return fail("null argument");
-  if (check_hw(T, in_c, H, W, noise_map != nullptr || h->use_sigma, h->cfg.in_ch)) return 1;
+  if (check_device(h)) return 1;
+  if (check_hw(T, in_c, H, W, noise_map != nullptr || o.use_sigma, h->cfg.in_ch)) return 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
   if (build_clip_plan(h, in, noise_map, out, T, in_c, H, W)) return 1;
@@ -943,18 +1007,18 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   }
   // stage 0 (input staging) is fused into temp1.inc.convblock.0 (first_conv.cuh)
   h->plan[0].first_in = in; h->plan[0].first_nmap = noise_map; h->plan[0].first_inc = in_c;
-  h->plan[0].first_u8 = h->u8_io; h->plan[0].first_norm = h->u8_io ? h->d_norm : nullptr;
+  h->plan[0].first_u8 = o.u8_io; h->plan[0].first_norm = o.u8_io ? h->d_norm : nullptr;
   if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   int launches = 0;
-  h->plan[15].p.resid_in = h->u8_io ? h->d_norm : in;   // temp1 residual reads the raw input (skip1)
-  h->plan[15].p.resid_C = h->u8_io ? 3 : in_c;
+  h->plan[15].p.resid_in = o.u8_io ? h->d_norm : in;   // temp1 residual reads the raw input (skip1)
+  h->plan[15].p.resid_C = o.u8_io ? 3 : in_c;
   h->plan[BSVD_NUM_LAYERS - 1].p.out = out;
-  // raw-image view of the first / residual / last kernels (bsvd_denoise_clip sets h->src_*)
+  // raw-image view of the first / residual / last kernels (the fused caller entries)
   for (int l : {0, 15, BSVD_NUM_LAYERS - 1}) {
     ConvParams& q = h->plan[l].p;
-    q.src_H = h->src_H; q.src_W = h->src_W;
-    q.use_sigma = h->use_sigma; q.sigma_const = h->sigma_const; q.clamp01 = h->clamp01;
-    q.u8_bgr = h->u8_bgr; q.out_u8 = h->u8_io;
+    q.src_H = o.src_H; q.src_W = o.src_W;
+    q.use_sigma = o.use_sigma; q.sigma_const = o.sigma_const; q.clamp01 = o.clamp01;
+    q.u8_bgr = o.u8_bgr; q.out_u8 = o.u8_io;
   }
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
     if (launch_stage(h->plan[l], st)) return 1;
@@ -965,8 +1029,16 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   return 0;
 }
 
-int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
-                      void* stream) {
+int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out, int T,
+                      int in_c, int H, int W, void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  if (check_dev_ptr(h, in, "in") || check_dev_ptr(h, noise_map, "noise_map") || check_dev_ptr(h, out, "out"))
+    return 1;
+  return forward_clip_impl(h, in, noise_map, out, T, in_c, H, W, stream, CallOpts());
+}
+
+static int denoise_clip_impl(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
+                             void* stream, CallOpts o) {
   if (!h || !in || !out) return fail("null argument");
   if (H < 2 || W < 2) return fail("reflect padding needs H, W >= 2 (got %dx%d)", H, W);
   const bool blind = h->cfg.in_ch == 3;
@@ -974,16 +1046,22 @@ int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, 
     return fail(blind ? "blind model: pass sigma < 0" : "non-blind model needs sigma >= 0");
   const int Hp = (H + 3) / 4 * 4, Wp = (W + 3) / 4 * 4;
   if (Hp - H >= H || Wp - W >= W) return fail("image too small to reflect-pad to a multiple of 4");
-  h->src_H = H; h->src_W = W; h->use_sigma = blind ? 0 : 1; h->sigma_const = sigma; h->clamp01 = 1;
+  o.src_H = H; o.src_W = W; o.use_sigma = blind ? 0 : 1; o.sigma_const = sigma; o.clamp01 = 1;
   // a 3-channel raw input: the 4th (noise-map) slot is synthesised by the first kernel
-  const int rc = bsvd_forward_clip(h, in, nullptr, out, T, 3, Hp, Wp, stream);
-  h->src_H = h->src_W = 0; h->use_sigma = 0; h->clamp01 = 0;
-  return rc;
+  return forward_clip_impl(h, in, nullptr, out, T, 3, Hp, Wp, stream, o);
+}
+
+int bsvd_denoise_clip(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,
+                      void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  if (check_dev_ptr(h, in, "in") || check_dev_ptr(h, out, "out")) return 1;
+  return denoise_clip_impl(h, in, sigma, out, T, H, W, stream, CallOpts());
 }
 
 int bsvd_denoise_clip_u8(bsvd_handle* h, const uint8_t* in, float sigma, uint8_t* out, int T, int H,
                          int W, int bgr, void* stream) {
   if (!h || !in || !out) return fail("null argument");
+  if (check_device(h) || check_dev_ptr(h, in, "in") || check_dev_ptr(h, out, "out")) return 1;
   const size_t need = (size_t)T * 3 * H * W * sizeof(float);
   if (h->d_norm_bytes < need) {
     if (h->d_norm) cudaFree(h->d_norm);
@@ -991,11 +1069,10 @@ int bsvd_denoise_clip_u8(bsvd_handle* h, const uint8_t* in, float sigma, uint8_t
     CUDA_TRY(cudaMalloc((void**)&h->d_norm, need));
     h->d_norm_bytes = need;
   }
-  h->u8_io = 1; h->u8_bgr = bgr ? 1 : 0;
-  const int rc = bsvd_denoise_clip(h, reinterpret_cast<const float*>(in), sigma,
-                                   reinterpret_cast<float*>(out), T, H, W, stream);
-  h->u8_io = 0; h->u8_bgr = 0;
-  return rc;
+  CallOpts o;
+  o.u8_io = 1; o.u8_bgr = bgr ? 1 : 0;
+  return denoise_clip_impl(h, reinterpret_cast<const float*>(in), sigma, reinterpret_cast<float*>(out), T, H,
+                           W, stream, o);
 }
 
 // ---- PSNR per frame (calculate_psnr_float, BasicSR/basicsr/metrics/psnr_ssim.py:130-168) -----------
@@ -1064,6 +1141,7 @@ static int ensure_dev(float** p, size_t* cur, size_t need) {
 int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nmap_host,
                            float* out_host, int T, int in_c, int H, int W, void* stream) {
   if (!h || !in_host || !out_host) return fail("null argument");
+  if (check_device(h)) return 1;
   if (check_hw(T, in_c, H, W, nmap_host != nullptr, h->cfg.in_ch)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t plane = (size_t)H * W * sizeof(float);
@@ -1087,6 +1165,7 @@ int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* nm
 int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const float* nmap_host,
                                  float* out_host, int T, int in_c, int H, int W, void* stream) {
   if (!h || !in_host || !out_host) return fail("null argument");
+  if (check_device(h)) return 1;
   if (check_hw(T, in_c, H, W, nmap_host != nullptr, h->cfg.in_ch)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!h->s_h2d) {
@@ -1122,6 +1201,13 @@ int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const flo
   CUDA_TRY(cudaMemcpyAsync(out_host, h->pout[k], plane * T * 3, cudaMemcpyDeviceToHost, h->s_d2h));
   CUDA_TRY(cudaEventRecord(h->ev_d2h[k], h->s_d2h));
   ++h->host_calls;
+  return 0;
+}
+
+int bsvd_host_last_output(bsvd_handle* h, float** dev_out) {
+  if (!h || !dev_out) return fail("null argument");
+  if (!h->host_calls) return fail("no bsvd_forward_clip_host_async call has been made on this handle");
+  *dev_out = h->pout[(h->host_calls - 1) & 1];
   return 0;
 }
 
@@ -1176,6 +1262,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       const size_t in_bytes = ring_slot_bytes(h, in_ring, H, W);
       StageIO io;
       io.T = 1; io.H = H / r; io.W = W / r;
+      io.overflow = h->d_overflow;
       io.in = S.ring[in_blk][in_ring];
       io.out = S.ring[b][kLayerOut[l]];          // patched per step
       io.ring_mode = sd.spec.shift ? 1 : 0;
@@ -1209,6 +1296,9 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
                      int in_c, int H, int W, int* produced, void* stream) {
   if (produced) *produced = 0;
   if (!h || !out) return fail("null argument");
+  if (check_device(h) || check_dev_ptr(h, frame, "frame") || check_dev_ptr(h, noise_map, "noise_map") ||
+      check_dev_ptr(h, out, "out"))
+    return 1;
   if (check_hw(1, frame ? in_c : h->cfg.in_ch, H, W, frame ? noise_map != nullptr : false, h->cfg.in_ch)) return 1;
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l)
     if (!h->stages[l].loaded) return fail("weights of layer %d were never set", l);
@@ -1292,7 +1382,7 @@ int bsvd_reset(bsvd_handle* h) {
 }
 
 // ---- single-stage hook -------------------------------------------------------------------------
-static float g_last_stage_ms = 0.f;
+static thread_local float g_last_stage_ms = 0.f;
 float bsvd_last_stage_ms(void) { return g_last_stage_ms; }
 int bsvd_conv_stage(const bsvd_conv_desc* d, const void* in, const float* w, const float* bias,
                     const void* skip, void* out, void* stream) {

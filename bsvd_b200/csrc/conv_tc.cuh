@@ -123,6 +123,10 @@ struct ConvParams {
   int clamp01;
   int u8_bgr;           // uint8 HWC frame I/O (bsvd_denoise_clip_u8): 1 = channel order B,G,R
   int out_u8;           // last kernel: store round(clamp(x) * 255) as uint8 [T][H][W][3] (tensor2img)
+  // fp16 storage has no headroom beyond 65504: stages whose output is not clamped by ReLU6 (the
+  // PixelShuffle + skip convs, temp1's output, every stage of an act='relu' model) set this sticky flag
+  // when a value they store is inf/NaN, so an overflow can never pass silently (bsvd_overflow_flag)
+  unsigned* overflow;
 };
 // reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
 __device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }
@@ -465,6 +469,7 @@ struct EpiParams {
   int src_H, src_W;
   void* out; void* out_prev; void* out_next; void* aux_out;
   const void* skip; const float* resid_in;
+  unsigned* overflow;
   long long out_frame_stride, skip_frame_stride;
   __device__ __forceinline__ explicit EpiParams(const ConvParams& p)
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
@@ -473,7 +478,7 @@ struct EpiParams {
         out_t0(p.out_t0), stg_bytes_per_warp(p.stg_bytes_per_warp),
         src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : p.W),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
-        resid_in(p.resid_in), out_frame_stride(p.out_frame_stride),
+        resid_in(p.resid_in), overflow(p.overflow), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
 };
 
@@ -622,6 +627,18 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       } else if (flags & EPI_RELU) {
         o[j].x = relu_packed<BF16>(o[j].x); o[j].y = relu_packed<BF16>(o[j].y);
         o[j].z = relu_packed<BF16>(o[j].z); o[j].w = relu_packed<BF16>(o[j].w);
+      }
+    }
+    if constexpr (!BF16) {
+      // fp16 range guard (see ConvParams::overflow): exponent field all ones in either half
+      if (!(flags & EPI_RELU6) && p.overflow) {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bad |= ((o[j].x & 0x7fff7fffu) + 0x04000400u) | ((o[j].y & 0x7fff7fffu) + 0x04000400u) |
+                 ((o[j].z & 0x7fff7fffu) + 0x04000400u) | ((o[j].w & 0x7fff7fffu) + 0x04000400u);
+        }
+        if (__any_sync(0xffffffffu, valid && (bad & 0x80008000u)) && lane == 0) atomicOr(p.overflow, 1u);
       }
     }
     if constexpr ((MASK & EPI_TMA_OUT) != 0) {

@@ -6,20 +6,14 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstring>
 
+#include "common.cuh"
 #include "conv_tc.cuh"
 
 namespace bsvd {
 
-// defined in bsvd_capi.cu: records the message bsvd_last_error() returns, yields 1
-int fail(const char* fmt, ...);
-#define CUDA_TRY(expr)                                                                       \
-  do {                                                                                       \
-    cudaError_t _e = (expr);                                                                 \
-    if (_e != cudaSuccess)                                                                   \
-      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-  } while (0)
 
 // dynamic shared memory: 227 KB opt-in limit minus the kernel's static shared (barriers, bias)
 constexpr size_t kSmemOptIn = 232448 - 3072;
@@ -67,7 +61,7 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
 }
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
 static int launch_pipe(const StageLaunch& L, cudaStream_t st) {
-  static bool attr_done[64] = {};      // per device: the attribute is per (function, device)
+  static std::atomic<bool> attr_done[64];      // per device: the attribute is per (function, device)
   auto kern = conv3x3_tc_kernel<NTILE, R, BF16, CTA2, MASK, EW, PIPE>;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -1,0 +1,188 @@
+"""Multi-GPU plumbing on top of the peer-memory C ABI (bsvd_peer_*, bsvd_b200/csrc/peer.cu).
+
+One process per GPU on one node (torchrun).  torch.distributed (NCCL) is the control plane —
+rendezvous, exchanging the CUDA-IPC handles, barriers, the timing reduction; the DATA moves with
+copy-engine copies between peer-mapped buffers over NVLink, on a side stream, with flag words for
+completion.  No SM is used by a transfer, so it overlaps the persistent conv kernels (one CTA per SM on
+all 148 SMs) without taking SMs away from them — an NCCL all_gather issued next to them either waits
+for the step to finish or, once resident, makes the stage kernels run in two waves.
+
+    group = PeerGroup(nbytes, nflags)                # collective: every rank calls it
+    gather = ClipGather(group_or_None, shape)        # ring of 2 slots of [world, *shape] per rank
+    gather.put(y, step)                              # after the forward that produced y (any stream)
+    g = gather.wait(step)                            # current stream waits; returns the [world, *shape] view
+
+The reference's counterpart is DataParallel's scatter/gather (BasicSR/basicsr/models/base_model.py:74-75).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import capi
+
+
+class PeerGroup:
+    """A symmetric device buffer (data + flags) on every rank, mapped into every other rank."""
+
+    def __init__(self, nbytes: int, nflags: int, group=None):
+        import torch.distributed as dist
+        self.lib = capi.load_library()
+        self.dist_group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.nbytes, self.nflags = int(nbytes), int(nflags)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        capi.check(self.lib.bsvd_peer_create(self.rank, self.world, self.nbytes, self.nflags, C.byref(h)))
+        self._h = h
+        if self.world > 1:
+            hb = self.lib.bsvd_peer_handle_bytes()
+            mine = (C.c_ubyte * hb)()
+            capi.check(self.lib.bsvd_peer_get_handle(self._h, mine))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            allh = torch.empty((self.world, hb), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, t, group=group)
+            buf = (C.c_ubyte * (hb * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+            capi.check(self.lib.bsvd_peer_open(self._h, buf))
+            dist.barrier(group=group)          # nobody puts before everybody has mapped
+        self.data_ptr = int(self.lib.bsvd_peer_local_data(self._h))
+        self.side = torch.cuda.Stream(device=self.device)      # transfers are enqueued here
+
+    # ---- views ---------------------------------------------------------------------------------
+    def local_tensor(self, offset: int, shape, dtype=torch.float32) -> torch.Tensor:
+        """A torch view of the local data area (no copy; lives as long as the group)."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        esz = torch.empty((), dtype=dtype).element_size()
+        if offset < 0 or offset + n * esz > self.nbytes:
+            raise ValueError("view outside the peer buffer")
+        arr = (C.c_ubyte * (n * esz)).from_address(self.data_ptr + offset)
+
+        class _Holder:        # __cuda_array_interface__ provider
+            pass
+        hold = _Holder()
+        typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+        hold.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
+                                         "data": (self.data_ptr + offset, False), "version": 2}
+        hold._keep = (self, arr)
+        return torch.as_tensor(hold, device=self.device)
+
+    # ---- one-sided operations ------------------------------------------------------------------
+    def put(self, dst_rank: int, dst_off: int, src: torch.Tensor, stream=None):
+        assert src.is_cuda and src.is_contiguous()
+        st = (stream or self.side).cuda_stream
+        capi.check(self.lib.bsvd_peer_put(self._h, dst_rank, dst_off, src.data_ptr(),
+                                          src.numel() * src.element_size(), st))
+
+    def put2d(self, dst_rank: int, dst_off: int, dst_pitch: int, src_ptr: int, src_pitch: int,
+              width_bytes: int, rows: int, stream=None):
+        st = (stream or self.side).cuda_stream
+        capi.check(self.lib.bsvd_peer_put2d(self._h, dst_rank, dst_off, dst_pitch, src_ptr, src_pitch,
+                                            width_bytes, rows, st))
+
+    def put3d(self, dst_rank: int, dst_off: int, dst_pitch: int, dst_plane_rows: int, src_ptr: int,
+              src_pitch: int, src_plane_rows: int, width_bytes: int, rows: int, planes: int, stream=None):
+        st = (stream or self.side).cuda_stream
+        capi.check(self.lib.bsvd_peer_put3d(self._h, dst_rank, dst_off, dst_pitch, dst_plane_rows, src_ptr,
+                                            src_pitch, src_plane_rows, width_bytes, rows, planes, st))
+
+    def signal(self, dst_rank: int, flag: int, value: int, stream=None):
+        st = (stream or self.side).cuda_stream
+        capi.check(self.lib.bsvd_peer_signal(self._h, dst_rank, flag, value, st))
+
+    def wait(self, flag: int, value: int, stream=None):
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        capi.check(self.lib.bsvd_peer_wait(self._h, flag, value, st))
+
+    def read_flag(self, flag: int) -> int:
+        v = C.c_uint(0)
+        capi.check(self.lib.bsvd_peer_read_flag(self._h, flag, C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.barrier(group=self.dist_group)     # peers may still be writing into / reading from us
+            self.lib.bsvd_peer_destroy(self._h)
+            self._h = None
+
+
+def gather_layout(world: int, slot_bytes: int, depth: int = 2):
+    """Offsets of the gather ring inside a rank's symmetric buffer and its flag indices.
+
+    data : [depth][world][slot_bytes]            slot (k, r) = clip of rank r for steps with step % depth == k
+    flags: ready[k][r]  (index k*world + r)      rank r's clip of slot k has landed   (value = step + 1)
+           free [k][r]  (index depth*world + k*world + r)   rank r has consumed slot k (value = step + 1)
+    """
+    return {"bytes": depth * world * slot_bytes, "nflags": 2 * depth * world,
+            "data": lambda k, r: (k * world + r) * slot_bytes,
+            "ready": lambda k, r: k * world + r,
+            "free": lambda k, r: depth * world + k * world + r}
+
+
+class ClipGather:
+    """All ranks end up with every rank's output clip: an all-gather done with copy engines.
+
+    put(y, step): the producing stream's work so far is awaited by the side stream, which then (1) waits
+    until every peer has released slot step % depth (their `free` flag from step - depth), (2) copies y
+    into slot (step % depth, rank) of EVERY rank (its own included) and (3) raises ready[k][rank] there.
+    wait(step): the calling stream waits for all `world` ready flags of the slot and gets the view.
+    release(step): the calling stream's reads of the slot are done — tell the producers.
+    """
+
+    def __init__(self, shape, dtype=torch.float32, depth: int = 2, group=None):
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.shape, self.dtype, self.depth = tuple(int(s) for s in shape), dtype, depth
+        n = 1
+        for s in self.shape:
+            n *= s
+        self.slot_bytes = n * torch.empty((), dtype=dtype).element_size()
+        self.lay = gather_layout(world, self.slot_bytes, depth)
+        self.pg = PeerGroup(self.lay["bytes"], self.lay["nflags"], group)
+        self.world, self.rank = self.pg.world, self.pg.rank
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_rel = torch.cuda.Event()
+        self.ev_put = [torch.cuda.Event() for _ in range(depth)]
+
+    def put(self, y: torch.Tensor, step: int):
+        assert tuple(y.shape) == self.shape and y.dtype == self.dtype and y.is_contiguous()
+        pg, k = self.pg, step % self.depth
+        ev = self.ev[k]
+        ev.record(torch.cuda.current_stream(pg.device))
+        pg.side.wait_event(ev)
+        if step >= self.depth:
+            for r in range(self.world):              # slot k was last used by step - depth
+                pg.wait(self.lay["free"](k, r), step - self.depth + 1, stream=pg.side)
+        for i in range(self.world):                  # start with the next rank: spreads the NVSwitch load
+            r = (self.rank + 1 + i) % self.world
+            pg.put(r, self.lay["data"](k, self.rank), y, stream=pg.side)
+            pg.signal(r, self.lay["ready"](k, self.rank), step + 1, stream=pg.side)
+        y.record_stream(pg.side)
+        done = self.ev_put[k]
+        done.record(pg.side)          # y has been read: its owner may overwrite it after this event
+        return done
+
+    def wait(self, step: int) -> torch.Tensor:
+        k = step % self.depth
+        for r in range(self.world):
+            self.pg.wait(self.lay["ready"](k, r), step + 1)
+        return self.pg.local_tensor(self.lay["data"](k, 0), (self.world,) + self.shape, self.dtype)
+
+    def release(self, step: int):
+        """Reads of slot `step` enqueued on the current stream so far are the last ones."""
+        pg, k = self.pg, step % self.depth
+        self.ev_rel.record(torch.cuda.current_stream(pg.device))
+        pg.side.wait_event(self.ev_rel)
+        for r in range(self.world):
+            pg.signal(r, self.lay["free"](k, self.rank), step + 1, stream=pg.side)
+
+    def close(self):
+        self.pg.close()

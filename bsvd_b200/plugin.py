@@ -76,9 +76,15 @@ def run_reference_script(path: str, reference_root: str):
     import runpy
     sys.path.append(os.path.join(reference_root, "BasicSR"))
     sys.path.append(reference_root)
+    import atexit
+    import json
+    reference_root = os.path.abspath(reference_root)
     stub_optional_dependencies()
     install()
+    from .arch import BSVD
+    atexit.register(lambda: print("bsvd_b200.plugin: " + json.dumps(BSVD.stats), flush=True))
     os.chdir(reference_root)
+    sys.argv = [os.path.join(reference_root, path)] + sys.argv[3:]
     runpy.run_path(os.path.join(reference_root, path), run_name="__main__")
 
 

@@ -1,9 +1,12 @@
 """Spatial-tile mode for frames too large for one GPU's time budget (BASELINE config 5: 4K clips).
 
-The frame is cut into rows x cols tiles, one per GPU (one process per GPU).  Each rank gathers
-the input pixels of a `HALO`-pixel (80) ring around its tile from its neighbours (one NCCL all_gather of
-the 4-channel input tiles over NVLink — the input is the only tensor that ever crosses GPUs), runs
-the unmodified BSVD-64 path on the enlarged tile and keeps the centre.
+The frame is cut into rows x cols tiles, one per GPU (one process per GPU).  Each rank receives
+the input pixels of a `HALO`-pixel (80) ring around its tile from the (up to 8) neighbours that own
+them — `TileExchange`: copy-engine puts into the neighbour's peer-mapped buffer over NVLink, only the
+strips that are needed, the 4-channel input being the only tensor that ever crosses GPUs — runs the
+unmodified BSVD-64 path on the enlarged tile and writes the centre of its output straight into the
+owner's full frame.  (`forward_tiled_distributed` is the older variant that all_gathers whole tiles
+through NCCL; it is kept for the CPU/gloo test of the paste logic.)
 
 Why this is exact: the receptive field of one DenBlock reaches 40 px (full-res convs 2+2, stride-2
 convs 1+2, half-res 4+6, quarter-res 20, and the two PixelShuffles, whose sub-pixel of a coarse cell
@@ -120,3 +123,134 @@ def forward_tiled_distributed(forward, x_tile: torch.Tensor, H: int, W: int, row
     for t, o in zip(tiles, outs):
         full[:, :, t.y0:t.y1, t.x0:t.x1] = o[:, :, :t.y1 - t.y0, :t.x1 - t.x0]
     return full
+
+
+# ---------------------------------------------------------------------------------------------------
+# neighbour-only exchange over NVLink (peer-mapped memory, copy engines)
+# ---------------------------------------------------------------------------------------------------
+def overlap(a: Tile, b: Tile):
+    """Part of tile a's OWN pixels that falls inside tile b's enlarged region: (ya, yb, xa, xb) or None."""
+    ya, yb = max(a.y0, b.hy0), min(a.y1, b.hy1)
+    xa, xb = max(a.x0, b.hx0), min(a.x1, b.hx1)
+    return (ya, yb, xa, xb) if ya < yb and xa < xb else None
+
+
+def exchange_plan(tiles):
+    """sends[r] = [(dst, ya, yb, xa, xb)]: the strips rank r owns that rank dst needs (dst == r: its own
+    centre).  Only tiles whose regions actually overlap appear: at most 8 neighbours + self."""
+    sends = []
+    for r, a in enumerate(tiles):
+        lst = []
+        for d, b in enumerate(tiles):
+            o = overlap(a, b)
+            if o is not None:
+                lst.append((d,) + o)
+        sends.append(lst)
+    recv_from = [[r for r, lst in enumerate(sends) if any(d == me for d, *_ in lst)] for me in range(len(tiles))]
+    return sends, recv_from
+
+
+class TileExchange:
+    """One spatial tile per rank; per step: neighbours' strips in, forward on the enlarged tile, centre
+    out to the owner rank's full frame.  All transfers are bsvd_peer_put3d copies on the side stream
+    (one per neighbour: [T*C planes][rows][cols] in a single copy-engine transfer), ordered by flags:
+
+      in_ready [k][src]   on dst : src's strip for slot k has landed              (value step+1)
+      in_free  [k][dst]   on src : dst's forward has consumed its region slot k   (value step+1)
+      out_ready[k][src]   on owner: src's centre is in full-frame slot k
+      out_free [k]        on all  : the owner has consumed full-frame slot k
+    """
+
+    def __init__(self, T, C, H, W, rows, cols, halo: int = HALO, owner: int = 0, depth: int = 2, group=None):
+        from .peer import PeerGroup
+        import torch.distributed as dist
+        self.T, self.C, self.H, self.W, self.depth, self.owner = T, C, H, W, depth, owner
+        self.tiles = tile_plan(H, W, rows, cols, halo)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world != len(self.tiles):
+            raise ValueError(f"{len(self.tiles)} tiles need {len(self.tiles)} ranks, got {world}")
+        self.sends, self.recv_from = exchange_plan(self.tiles)
+        rh = max(t.hy1 - t.hy0 for t in self.tiles)
+        rw = max(t.hx1 - t.hx0 for t in self.tiles)
+        self.region_bytes = (T * C * rh * rw * 4 + 1023) // 1024 * 1024
+        self.full_bytes = (T * 3 * H * W * 4 + 1023) // 1024 * 1024
+        self.off_region = lambda k: k * self.region_bytes
+        self.off_full = lambda k: depth * self.region_bytes + k * self.full_bytes
+        nbytes = depth * (self.region_bytes + self.full_bytes)
+        w = world
+        self.f_in_ready = lambda k, src: k * w + src
+        self.f_in_free = lambda k, dst: depth * w + k * w + dst
+        self.f_out_ready = lambda k, src: 2 * depth * w + k * w + src
+        self.f_out_free = lambda k: 3 * depth * w + k
+        self.pg = PeerGroup(nbytes, 3 * depth * w + depth, group)
+        self.rank, self.world = self.pg.rank, world
+        self.me = self.tiles[self.rank]
+        self.ev_in = torch.cuda.Event()
+        self.ev_fwd = torch.cuda.Event()
+        self.ev_own = torch.cuda.Event()
+        me = self.me
+        self.ring_bytes = T * C * 4 * ((me.hy1 - me.hy0) * (me.hx1 - me.hx0) - (me.y1 - me.y0) * (me.x1 - me.x0))
+        self.received_bytes = 0
+
+    def step(self, forward, x_tile: torch.Tensor, step: int):
+        """x_tile: this rank's [T,C,th,tw] fp32 input tile (device, contiguous).  Enqueues the whole step;
+        returns the owner's full-frame view [T,3,H,W] of this step on the owner rank (valid after
+        `wait_full(step)`), None elsewhere."""
+        pg, k, me, T, C = self.pg, step % self.depth, self.me, self.T, self.C
+        th, tw = me.y1 - me.y0, me.x1 - me.x0
+        assert tuple(x_tile.shape) == (T, C, th, tw) and x_tile.is_contiguous() and x_tile.dtype == torch.float32
+        cur = torch.cuda.current_stream(pg.device)
+        self.ev_in.record(cur)
+        pg.side.wait_event(self.ev_in)
+        for dst, ya, yb, xa, xb in self.sends[self.rank]:
+            d = self.tiles[dst]
+            dh, dw = d.hy1 - d.hy0, d.hx1 - d.hx0
+            if step >= self.depth:
+                pg.wait(self.f_in_free(k, dst), step - self.depth + 1, stream=pg.side)
+            src_ptr = x_tile.data_ptr() + ((ya - me.y0) * tw + (xa - me.x0)) * 4
+            dst_off = self.off_region(k) + ((ya - d.hy0) * dw + (xa - d.hx0)) * 4
+            pg.put3d(dst, dst_off, dw * 4, dh, src_ptr, tw * 4, th, (xb - xa) * 4, yb - ya, T * C, stream=pg.side)
+            pg.signal(dst, self.f_in_ready(k, self.rank), step + 1, stream=pg.side)
+        x_tile.record_stream(pg.side)
+        # ---- forward on the enlarged tile once every contributor's strip has landed
+        for src in self.recv_from[self.rank]:
+            pg.wait(self.f_in_ready(k, src), step + 1)
+            if src != self.rank and step == 0:
+                ya, yb, xa, xb = overlap(self.tiles[src], me)
+                self.received_bytes += T * C * 4 * (yb - ya) * (xb - xa)
+        hh, ww = me.hy1 - me.hy0, me.hx1 - me.hx0
+        region = pg.local_tensor(self.off_region(k), (T, C, hh, ww))
+        y = forward(region)                                    # [T,3,hh,ww]
+        self.ev_fwd.record(cur)
+        pg.side.wait_event(self.ev_fwd)
+        for src in self.recv_from[self.rank]:                  # my region slot k may be refilled
+            pg.signal(src, self.f_in_free(k, self.rank), step + 1, stream=pg.side)
+        # ---- centre of the output straight into the owner's full frame
+        if step >= self.depth:
+            pg.wait(self.f_out_free(k), step - self.depth + 1, stream=pg.side)
+        y = y.contiguous()
+        src_ptr = y.data_ptr() + ((me.y0 - me.hy0) * ww + (me.x0 - me.hx0)) * 4
+        dst_off = self.off_full(k) + (me.y0 * self.W + me.x0) * 4
+        pg.put3d(self.owner, dst_off, self.W * 4, self.H, src_ptr, ww * 4, hh, tw * 4, th, T * 3, stream=pg.side)
+        pg.signal(self.owner, self.f_out_ready(k, self.rank), step + 1, stream=pg.side)
+        y.record_stream(pg.side)
+        if self.rank == self.owner:
+            return pg.local_tensor(self.off_full(k), (T, 3, self.H, self.W))
+        return None
+
+    def wait_full(self, step: int):
+        """Owner: the calling stream waits until every rank's centre of `step` has landed."""
+        k = step % self.depth
+        for src in range(self.world):
+            self.pg.wait(self.f_out_ready(k, src), step + 1)
+
+    def release_full(self, step: int):
+        """Owner: reads of the full frame of `step` enqueued on the current stream so far are the last."""
+        pg, k = self.pg, step % self.depth
+        self.ev_own.record(torch.cuda.current_stream(pg.device))
+        pg.side.wait_event(self.ev_own)
+        for r in range(self.world):
+            pg.signal(r, self.f_out_free(k), step + 1, stream=pg.side)
+
+    def close(self):
+        self.pg.close()

@@ -12,6 +12,11 @@
  * cudaStream_t passed as void* (0 = legacy default stream).  Every call returns 0 on success,
  * non-zero on failure; bsvd_last_error() returns a description of the last failure of the
  * calling thread.  Nothing here ever falls back to a CPU path.
+ *
+ * Threading and devices: a handle is bound to the CUDA device it was created on (weights, workspaces,
+ * tensor maps); every entry point fails if another device is current or a device pointer lives
+ * elsewhere.  A handle caches its launch plan and workspaces, so calls on ONE handle must not run
+ * concurrently from several host threads (use one handle per thread); different handles are independent.
  */
 #ifndef BSVD_B200_H_
 #define BSVD_B200_H_
@@ -68,7 +73,8 @@ const char* bsvd_version(void);
  *  11 upc1.memconv.c1     12 upc1.memconv.c2       13 upc1.convblock.0 (+PixelShuffle)
  *  14 outc.convblock.0    15 outc.convblock.3
  * w is the nn.Conv2d weight, HOST pointer, fp32, OIHW contiguous; bias HOST fp32 [O].
- * The call repacks into the tensor-core layout and uploads (synchronous). */
+ * The call repacks into the tensor-core layout and uploads (synchronous; when the layer already held
+ * weights the device is drained first, so a forward still in flight on any stream never sees a mix). */
 int bsvd_set_weights(bsvd_handle* h, int layer, const float* w_oihw, const float* bias,
                      int out_ch, int in_ch);
 /* expected (out_ch, in_ch) of a layer; returns non-zero for a bad index */
@@ -126,6 +132,10 @@ int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* no
 int bsvd_forward_clip_host_async(bsvd_handle* h, const float* in_host, const float* noise_map_host,
                                  float* out_host, int T, int in_c, int H, int W, void* stream);
 int bsvd_host_sync(bsvd_handle* h);
+/* Device staging buffer ([T,3,H,W] fp32) holding the result of the most recent
+ * bsvd_forward_clip_host_async call, valid for consumers ordered behind that call on its stream and
+ * until the call after next reuses it (multi-GPU: the gather reads it from here, see bsvd_peer_*). */
+int bsvd_host_last_output(bsvd_handle* h, float** dev_out);
 
 /* -- streaming mode: BSVD.feedin_one_element / reset (bsvd_arch.py:485-488, 459-461) -------
  * frame:     device fp32 [in_c, H, W] or NULL (NULL = the reference's feedin_one_element(None))
@@ -136,9 +146,43 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
                      int in_c, int H, int W, int* produced, void* stream);
 int bsvd_reset(bsvd_handle* h);
 
+/* -- multi-GPU plumbing: one-sided exchange over NVLink through peer-mapped memory ---------
+ * replaces the reference's DataParallel scatter/gather (BasicSR/basicsr/models/base_model.py:74-75) for
+ * the two ways this path shards: independent clips, one per GPU (gathering the denoised clips), and 4K
+ * frames cut into spatial tiles (the input strips a tile needs from its neighbours).
+ * One process per GPU on one node.  Every rank owns a symmetric buffer of `bytes` data bytes and `nflags`
+ * 32-bit flags; peers map it through CUDA IPC (exchange the handles with any out-of-band channel, e.g.
+ * torch.distributed).  Transfers are copy-engine copies enqueued on `stream` — no SM is used, so they
+ * overlap the compute kernels entirely; a signal is a flag write ordered behind the puts of the same
+ * stream, a wait makes `stream` block until the LOCAL flag is >= value.  Signal values must increase. */
+typedef struct bsvd_peer_group bsvd_peer_group;
+int bsvd_peer_create(int rank, int world, size_t bytes, int nflags, bsvd_peer_group** out);
+int bsvd_peer_handle_bytes(void);                               /* size of one exported handle */
+int bsvd_peer_get_handle(bsvd_peer_group* g, void* handle_out); /* this rank's handle */
+int bsvd_peer_open(bsvd_peer_group* g, const void* handles);    /* world x handle_bytes, rank order */
+void* bsvd_peer_local_data(bsvd_peer_group* g);                 /* device pointer of the local data area */
+int bsvd_peer_put(bsvd_peer_group* g, int dst_rank, size_t dst_off, const void* src, size_t bytes, void* stream);
+int bsvd_peer_put2d(bsvd_peer_group* g, int dst_rank, size_t dst_off, size_t dst_pitch, const void* src,
+                    size_t src_pitch, size_t width_bytes, size_t rows, void* stream);
+/* planes x rows x width_bytes block between two pitched volumes (pitch in bytes, plane height in rows):
+ * e.g. the strip [T*C][rows][cols] of an NCHW clip into a neighbour's enlarged tile, one transfer */
+int bsvd_peer_put3d(bsvd_peer_group* g, int dst_rank, size_t dst_off, size_t dst_pitch, size_t dst_plane_rows,
+                    const void* src, size_t src_pitch, size_t src_plane_rows, size_t width_bytes, size_t rows,
+                    size_t planes, void* stream);
+int bsvd_peer_signal(bsvd_peer_group* g, int dst_rank, int flag, unsigned value, void* stream);
+int bsvd_peer_wait(bsvd_peer_group* g, int flag, unsigned value, void* stream);
+int bsvd_peer_read_flag(bsvd_peer_group* g, int flag, unsigned* value);   /* synchronous, for tests */
+int bsvd_peer_destroy(bsvd_peer_group* g);
+
 /* -- introspection used by bench.py / tests -------------------------------------------------- */
 /* number of kernel launches enqueued by the last forward/push on this handle */
 int bsvd_last_launch_count(const bsvd_handle* h);
+/* fp16 range guard.  Activations are stored in 16 bits; with BSVD_PREC_FP16 a stage whose output is not
+ * clamped by ReLU6 (the PixelShuffle + skip convs, temp1's output, every stage of an act='relu' model)
+ * could exceed 65504 where the reference's fp32 tensors (bsvd_arch.py:402-414) would not.  Such a store
+ * sets a sticky device flag; this call waits for the device, returns it through *flag (0 / 1) and
+ * clears it when reset != 0.  bf16 has fp32's range and never sets it. */
+int bsvd_overflow_flag(bsvd_handle* h, int* flag, int reset);
 /* bytes of device workspace currently held */
 size_t bsvd_workspace_bytes(const bsvd_handle* h);
 

@@ -439,3 +439,141 @@ def test_long_clip_crosses_2G_element_offsets():
         short_out = net(x[None, 40:])[0]
     assert torch.equal(tail, short_out[22:])
     assert bool(torch.isfinite(tail).all())
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: handle hygiene (weights reloaded after a forward, device binding, fp16 range guard)
+# ---------------------------------------------------------------------------------------------------
+def test_weights_changed_after_a_forward_take_effect_clip_and_stream():
+    """A cached launch plan carries the bias in the kernel-parameter bank: reloading a checkpoint after a
+    forward at the same shape must refresh it (net.load / load_state_dict / an optimizer step)."""
+    net, _ = make_net(seed=0)
+    x, _ = O.make_synthetic_clip(4, 32, 48, seed=21)
+    xc = x.cuda()
+    with torch.no_grad():
+        net(xc[None])                                           # plan for [4,32,48] is now cached
+        s0 = [net.feedin_one_element(xc[i:i + 1]) for i in range(2)]   # and the streaming templates
+        net.reset()
+        sd2 = O.make_synthetic_params(5, 0.5)
+        for k in sd2:
+            if k.endswith(".bias"):
+                sd2[k] = sd2[k] + 0.05                          # make stale biases clearly visible
+        net.load_tsn_state(sd2)
+        y = net(xc[None])[0].float().cpu()
+        outs = [net.feedin_one_element(xc[i:i + 1]) for i in range(4)]
+        while sum(o is not None for o in outs) < 4:
+            outs.append(net.feedin_one_element(None))
+        net.reset()
+    ref = O.forward_clip(O.layers_from_tsn_state(sd2), x)
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+    ys = torch.cat([o for o in outs if o is not None]).float().cpu()
+    assert torch.equal(ys, y)
+    # in-place parameter update (what an optimizer step / load_state_dict does)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.9)
+        y2 = net(xc[None])[0].float().cpu()
+    sd3 = {k: v * 0.9 for k, v in sd2.items()}
+    ref2 = O.forward_clip(O.layers_from_tsn_state(sd3), x)
+    assert float((y2 - ref2).abs().max()) <= TOL["fp16"]
+
+
+def test_fp16_range_guard_flags_overflow_and_bf16_does_not():
+    x, _ = O.make_synthetic_clip(2, 32, 48, seed=22)
+    sd = O.make_synthetic_params(0, 0.5)
+    # blow up the un-activated PixelShuffle conv of temp1's upc1 (its output is stored without ReLU6)
+    key = [k for k in sd if "nets_list.0.upc1.convblock.1.weight" in k][0]
+    sd_big = dict(sd)
+    sd_big[key] = sd[key] * 3.0e4
+    from bsvd_b200.arch import BSVD
+    for prec, want in (("fp16", True), ("bf16", False)):
+        net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+                   act='relu6', pretrain_ckpt=None, precision=prec)
+        net.load_tsn_state(sd_big)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            net(x[None].cuda())
+        assert net.overflowed() is want, prec
+        assert net.overflowed() is False                        # the read cleared it
+    net, _ = make_net()
+    with torch.no_grad():
+        net(x[None].cuda())
+    assert net.overflowed() is False                            # ordinary weights never trip it
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_handle_follows_the_module_to_another_device_and_rejects_foreign_pointers():
+    import ctypes as C
+    from bsvd_b200 import capi
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(3, 32, 48, seed=23)
+    with torch.no_grad():
+        a = net(x[None].cuda(0))[0].float().cpu()
+        net = net.to("cuda:1")
+        b = net(x[None].to("cuda:1"))[0]
+        assert b.device.index == 1
+        assert torch.equal(a, b.float().cpu())
+        c = net(x[None].cuda(0))[0]                             # input on GPU 0: handle is rebuilt there
+        assert c.device.index == 0 and torch.equal(a, c.float().cpu())
+    # C ABI: a handle of device 0 called while device 1 is current fails loudly
+    lib = capi.load_library()
+    xin = x.cuda(0).contiguous()
+    out = torch.empty((3, 3, 32, 48), device="cuda:0")
+    with torch.cuda.device(1):
+        rc = lib.bsvd_forward_clip(net._handle, xin.data_ptr(), None, out.data_ptr(), 3, 4, 32, 48, None)
+        assert rc != 0 and b"device" in lib.bsvd_last_error()
+    with torch.cuda.device(0):
+        bad = torch.empty((3, 3, 32, 48), device="cuda:1")
+        rc = lib.bsvd_forward_clip(net._handle, xin.data_ptr(), None, bad.data_ptr(), 3, 4, 32, 48, None)
+        assert rc != 0 and b"device" in lib.bsvd_last_error()
+
+
+def test_full_size_all_ten_frames_fp16_and_bf16_against_oracle():
+    """The benchmarked configuration end to end: every frame of the [1,10,4,540,960] clip."""
+    x, clean = O.make_synthetic_clip(10, 540, 960, seed=1)
+    sd = O.make_synthetic_params(0, 0.5)
+    ref = O.forward_clip(O.layers_from_tsn_state(sd), x)
+    for prec in ("fp16", "bf16"):
+        net, _ = make_net(prec=prec)
+        with torch.no_grad():
+            y = net(x[None].cuda())[0].float().cpu()
+        assert float((y - ref).abs().max()) <= TOL[prec], prec
+        assert not net.overflowed()
+        del net
+
+
+@pytest.mark.parametrize("shape", [(10, 36, 1028), (10, 132, 132), (10, 4, 4), (10, 540, 68)])
+def test_odd_tile_sizes_at_T10(shape):
+    """One ragged size per kernel family at the benchmarked clip length: widths that leave 4 / 1 / 36 px
+    in the last x-block at full / half / quarter resolution, a single-tile image, a tall narrow one."""
+    T, H, W = shape
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(T, H, W, seed=31)
+    with torch.no_grad():
+        y = net(x[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x)
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+
+
+def test_stream_100_frames_bf16_full_size_bit_identical_to_clip_prefix():
+    """BASELINE.json configs[2] at its real size: the streaming schedule (one push per frame, graph
+    replays in steady state) against the clip schedule on the same frames."""
+    net, _ = make_net(prec="bf16")
+    x, _ = O.make_synthetic_clip(6, 540, 960, seed=1)
+    pool = [x[i:i + 1].cuda() for i in range(6)]
+    n = 40
+    seq = [pool[i % 6] for i in range(n)]
+    with torch.no_grad():
+        outs, k = [], 0
+        for f in seq:
+            y = net.feedin_one_element(f)
+            if y is not None:
+                outs.append(y)
+        while len(outs) < n:
+            y = net.feedin_one_element(None)
+            if y is not None:
+                outs.append(y)
+        net.reset()
+        ys = torch.cat(outs)
+        yc = net(torch.cat(seq)[None])[0]
+    assert torch.equal(ys, yc)

@@ -1,0 +1,121 @@
+"""The UNMODIFIED reference in the loop on the B200 (staged under baseline/_ref by
+tools/stage_reference.py; the GPU box has no /root/reference).
+
+  * profile.py (the reference's headline harness, profile.py:55-83) runs unchanged, end to end, with
+    ARCH_REGISTRY['BSVD'] resolving to the B200 class (`python -m bsvd_b200.plugin baseline/_ref profile.py`)
+  * our output against the live reference BSVD through PyTorch/cuDNN with TF32 off on the same GPU, on
+    the benchmarked [1,10,4,540,960] clip, every frame
+  * the staged copy is byte-identical to what was staged (sha256 manifest)
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import bsvd_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import stage_reference  # noqa: E402
+from baseline import reference_runner as R  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="baseline/_ref not staged (python tools/stage_reference.py "
+                                                        "in the build container)")
+
+
+@needs_ref
+def test_staged_reference_is_unmodified():
+    assert stage_reference.verify(REF) > 50
+
+
+@needs_ref
+def test_profile_py_runs_unchanged_through_the_plugin(tmp_path):
+    ck = os.path.join(REF, "experiments", "pretrained_ckpt")
+    os.makedirs(ck, exist_ok=True)
+    torch.save({"params": O.make_synthetic_params(0, 0.5)}, os.path.join(ck, "bsvd-64.pth"))
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "bsvd_b200.plugin", REF, "profile.py"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    out = r.stdout + "\n" + r.stderr
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "profile_py_through_plugin.log"), "w") as f:
+        f.write(out)
+    assert r.returncode == 0, out[-4000:]
+    assert stage_reference.verify(REF) > 50                       # profile.py and the yml were not touched
+    m = re.search(r"bsvd_b200\.plugin: (\{.*\})", out)
+    assert m, out[-2000:]
+    stats = json.loads(m.group(1))
+    assert stats["instances"] >= 1 and stats["forward_calls"] >= 10, stats
+    assert stats["kernel_launches"] == 32 * stats["forward_calls"], stats
+    assert "B200-native BSVD-64" in out                           # print(model) shows our module
+    assert "output shape is torch.Size([1, 10, 3, 540, 960])" in out
+    t = re.findall(r"loops, mean of best \d+: ([0-9.]+) sec per loop", out)
+    assert t, out[-2000:]
+    assert float(t[-1]) < 0.05          # 10 frames at 540x960: ~10 ms; the reference itself needs ~52 ms in fp16
+
+
+@needs_ref
+def test_matches_live_reference_on_gpu_full_size_all_frames():
+    from bsvd_b200.arch import BSVD
+    sd = O.make_synthetic_params(0, 0.5)
+    x, clean = O.make_synthetic_clip(10, 540, 960, seed=1)
+    xd = x.cuda()
+    ref_net = R.build_reference_bsvd(sd, "cuda")
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = ref_net(xd[None])[0]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del ref_net
+    for prec, tol in (("fp16", 1e-3), ("bf16", 1e-2)):
+        net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+                   act='relu6', pretrain_ckpt=None, precision=prec)
+        net.load_tsn_state(sd)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            y = net(xd[None])[0]
+        err = float((y - ref).abs().max())
+        assert err <= tol, (prec, err)
+        assert not net.overflowed()
+        for t in (0, 4, 9):
+            d = abs(O.psnr_float(y[t].clamp(0, 1).cpu(), clean[t]) - O.psnr_float(ref[t].clamp(0, 1).cpu(), clean[t]))
+            assert d < 0.01, (prec, t, d)
+        del net
+
+
+@needs_ref
+def test_reference_stream_protocol_live_matches_ours():
+    """feedin_one_element call by call against the live reference class: same None pattern, same values."""
+    from bsvd_b200.arch import BSVD
+    sd = O.make_synthetic_params(3, 0.5)
+    x, _ = O.make_synthetic_clip(5, 36, 68, seed=12)
+    xd = x.cuda()
+    ref_net = R.build_reference_bsvd(sd, "cuda")
+    net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
+               act='relu6', pretrain_ckpt=None)
+    net.load_tsn_state(sd)
+    net = net.cuda().eval()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            feeds = [xd[i:i + 1] for i in range(5)] + [None] * 17
+            for i, f in enumerate(feeds):
+                a, b = ref_net.feedin_one_element(f), net.feedin_one_element(f)
+                assert (a is None) == (b is None), i
+                if a is not None:
+                    assert float((a - b).abs().max()) <= 1e-3, i
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        ref_net.reset()
+        net.reset()

@@ -77,3 +77,31 @@ def test_distributed_exchange_world2_gloo():
     full = _oracle_forward()(x)
     assert got.shape == full.shape
     assert float((got - full).abs().max()) < 2e-5
+
+
+def test_exchange_plan_strips_rebuild_every_enlarged_region():
+    """Neighbour-only exchange (TileExchange): the strips each rank sends, pasted at the receiver, are
+    exactly the receiver's enlarged region; nobody sends to a tile that does not need it; the bytes a
+    tile receives equal its ring."""
+    H, W = 176, 352
+    x = torch.arange(H * W, dtype=torch.float32).reshape(1, 1, H, W)
+    for rows, cols in ((1, 2), (2, 2), (2, 4), (4, 2)):
+        tiles = tiling.tile_plan(H, W, rows, cols)
+        sends, recv_from = tiling.exchange_plan(tiles)
+        for me, t in enumerate(tiles):
+            reg = torch.full((1, 1, t.hy1 - t.hy0, t.hx1 - t.hx0), -1.0)
+            got = 0
+            for src, lst in enumerate(sends):
+                for d, ya, yb, xa, xb in lst:
+                    if d == me:
+                        assert src in recv_from[me]
+                        reg[:, :, ya - t.hy0:yb - t.hy0, xa - t.hx0:xb - t.hx0] = x[:, :, ya:yb, xa:xb]
+                        if src != me:
+                            got += (yb - ya) * (xb - xa)
+            assert torch.equal(reg, x[:, :, t.hy0:t.hy1, t.hx0:t.hx1])
+            ring = (t.hy1 - t.hy0) * (t.hx1 - t.hx0) - (t.y1 - t.y0) * (t.x1 - t.x0)
+            assert got == ring
+    # 4K, 2x4: at most 8 neighbours + self, and far tiles exchange nothing
+    tiles = tiling.tile_plan(2160, 3840, 2, 4)
+    sends, _ = tiling.exchange_plan(tiles)
+    assert max(len(s) for s in sends) <= 9 and all(len(s) < len(tiles) for s in sends)
