@@ -99,6 +99,18 @@ class ClockSampler:
 # CPU baselines: the UNMODIFIED reference staged under baseline/_ref (tools/stage_reference.py), or —
 # only when that staging is absent — the oracle port (same torch CPU conv2d calls)
 # ------------------------------------------------------------------------------------------------
+class quiet_stdout:
+    """The reference prints (e.g. "load from <ckpt>"); stdout carries exactly ONE JSON line, so anything
+    printed while the reference runs is sent to stderr."""
+
+    def __enter__(self):
+        self._old = sys.stdout
+        sys.stdout = sys.stderr
+
+    def __exit__(self, *exc):
+        sys.stdout = self._old
+
+
 def reference_available():
     from baseline import reference_runner as R
     return R.available()
@@ -115,7 +127,8 @@ def cpu_forward_fps(frames, steps, warmup, budget_s=150.0):
     x, _ = O.make_synthetic_clip(frames, H, W, seed=1)
     if reference_available():
         from baseline import reference_runner as R
-        fps, s_pass, done, cores = R.time_cpu_forward(sd, x, steps, warmup, budget_s)
+        with quiet_stdout():
+            fps, s_pass, done, cores = R.time_cpu_forward(sd, x, steps, warmup, budget_s)
         return fps, s_pass, done, cores, "reference"
     layers = O.layers_from_tsn_state(sd)
     for _ in range(warmup):
@@ -333,6 +346,9 @@ def run_b200(args):
         after_forward(y)
         return y
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         y = step()
     drain()
@@ -352,11 +368,14 @@ def run_b200(args):
         del ref_g
         torch.cuda.synchronize()
 
-    # ---- timed region: K steps, profiling OFF (no events between the PDL-chained stage launches)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+    # ---- timed region: K steps, profiling OFF (no events between the PDL-chained stage launches).
+    # A few more warm-up steps run right before the bracket so that the board is in its sustained
+    # power-capped state when the timed region starts (measured, tools/probe_idle_gap.py: after a 0.25 s /
+    # 1 s pause the next 10 steps run 4 % / 7 % faster than back-to-back steps; 50 steps in a row are
+    # another 3 % slower than 10).
+    for _ in range(3):
+        y = step()
+    drain()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -380,6 +399,21 @@ def run_b200(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * T_CLIP * args.steps / (ms_total / 1e3)
+
+    # ---- the same K steps once more after a 250 ms idle pause (round 1's protocol paused there to let the
+    # clock sampler start).  Under the 1 kW power cap a pause lets the board boost for the next ~100 ms, so this
+    # figure is a BURST rate; `value` above is taken back to back after the warm-up steps (sustained).
+    value_after_idle = None
+    if world == 1:
+        torch.cuda.synchronize()
+        time.sleep(0.25)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            step()
+        b1.record()
+        torch.cuda.synchronize()
+        value_after_idle = T_CLIP * args.steps / (b0.elapsed_time(b1) / 1e3)
 
     # ---- per-stage timing in a SEPARATE pass (events between the launches defeat the PDL overlap)
     capi.check(lib.bsvd_set_profiling(net._handle, 1))
@@ -540,7 +574,8 @@ def run_b200(args):
     if world == 1:
         if reference_available() and not args.no_gpu_reference:
             try:
-                gpu_ref = gpu_reference_block(sd, x_dev, y_dev)
+                with quiet_stdout():
+                    gpu_ref = gpu_reference_block(sd, x_dev, y_dev)
                 gpu_ref["speedup_value_vs_fp16"] = value / gpu_ref["fp16"]["value"]
                 gpu_ref["speedup_value_vs_tf32"] = value / gpu_ref["tf32"]["value"]
                 if gpu_ref["parity_vs_fp32"]["max_abs"] > tol:
@@ -586,6 +621,9 @@ def run_b200(args):
                 "path": "BSVD.denoise_host_async -> bsvd_forward_clip_host_async (pinned host buffers; every step's H2D and D2H copies are inside the timed region, overlapped across steps on copy streams)"
                         + ("; followed by the same gather as `value`" if world > 1 else ""),
                 "unpipelined_value": e2e_sync_fps, "checksum": e2e_check},
+        "value_after_250ms_idle": value_after_idle,
+        "timing_note": "value: K steps back to back right after the warm-up steps (no idle gap, sustained under the "
+                       "power cap); value_after_250ms_idle: round 1's protocol (pause before the timed region), a burst rate",
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -414,6 +414,10 @@ class BSVD(nn.Module):
         if getattr(self, "_handle", None) is not None:
             capi.check(capi.load_library().bsvd_reset(self._handle))
 
+    def stream_graph_replays(self):
+        """Streaming pushes served by replaying a captured CUDA graph (steady state) so far."""
+        return 0 if self._handle is None else int(capi.load_library().bsvd_stream_graph_replays(self._handle))
+
     def count_shift(self):
         return self.shift_num
 

@@ -26,7 +26,7 @@ EXPORTS = (
     "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
     "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info", "bsvd_last_stage_ms",
     "bsvd_forward_clip_host_async", "bsvd_host_sync", "bsvd_denoise_clip", "bsvd_psnr",
-    "bsvd_denoise_clip_u8", "bsvd_overflow_flag", "bsvd_host_last_output",
+    "bsvd_denoise_clip_u8", "bsvd_overflow_flag", "bsvd_host_last_output", "bsvd_stream_graph_replays", "bsvd_ssim",
     "bsvd_peer_create", "bsvd_peer_handle_bytes", "bsvd_peer_get_handle", "bsvd_peer_open",
     "bsvd_peer_local_data", "bsvd_peer_put", "bsvd_peer_put2d", "bsvd_peer_put3d", "bsvd_peer_signal", "bsvd_peer_wait",
     "bsvd_peer_read_flag", "bsvd_peer_destroy",
@@ -78,9 +78,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_host_last_output.argtypes = [vp, C.POINTER(vp)]
     lib.bsvd_denoise_clip.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, vp]
     lib.bsvd_psnr.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
+    lib.bsvd_ssim.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_float, vp, vp]
     lib.bsvd_denoise_clip_u8.argtypes = [vp, vp, C.c_float, vp, ci, ci, ci, ci, vp]
     lib.bsvd_stream_push.argtypes = [vp, vp, vp, vp, ci, ci, ci, cip, vp]
     lib.bsvd_reset.argtypes = [vp]
+    lib.bsvd_stream_graph_replays.argtypes = [vp]
+    lib.bsvd_stream_graph_replays.restype = C.c_longlong
     lib.bsvd_last_launch_count.argtypes = [vp]
     lib.bsvd_workspace_bytes.argtypes = [vp]
     lib.bsvd_workspace_bytes.restype = C.c_size_t

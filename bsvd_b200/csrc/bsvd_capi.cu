@@ -20,6 +20,7 @@
 #include "stage_launch.cuh"
 #include "final_conv.cuh"
 #include "first_conv.cuh"
+#include "metrics.cuh"
 
 namespace bsvd {
 
@@ -71,14 +72,15 @@ static int make_map_halo(CUtensorMap* m, const void* base, int T, int H, int W, 
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(halo) failed: %d", (int)r);
   return 0;
 }
-// Stride-2 view of the same tensor: [T][H/2][2][W/2][2*C]; box = [1][R][1][128][64] (one tap).
-static int make_map_s2(CUtensorMap* m, const void* base, int T, int H, int W, int C, int R) {
+// Stride-2 view of the same tensor: [T][H/2][2][W/2][2*C]; box = [1][R][1][box_px][64]: one tap
+// (box_px 128, generic pipeline) or one input sub-plane (box_px 129, R or R+1 rows; conv_tc.cuh PIPE 4).
+static int make_map_s2(CUtensorMap* m, const void* base, int T, int H, int W, int C, int R, int box_px = kRunPx) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)T};
   cuuint64_t strides[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2,
                            (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)kRunPx, 1, (cuuint32_t)R, 1};
+  cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)box_px, 1, (cuuint32_t)R, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -105,6 +107,26 @@ static int make_map_pix(CUtensorMap* m, const void* base, int T, long long t_str
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(pixel view) failed: %d", (int)r);
   return 0;
+}
+
+// Raw network input for the first conv's TMA loader: fp32 planes [planes][H][W]; box = [box_planes][4][132].
+static int make_map_raw(CUtensorMap* m, const void* base, long long planes, int H, int W, int box_planes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kRawPx, (cuuint32_t)kRawRows, (cuuint32_t)box_planes};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(raw input) failed: %d", (int)r);
+  return 0;
+}
+// The TMA path of the first conv needs 16-byte aligned planes (W % 4 == 0 holds for every network input).
+static bool raw_tma_ok(const void* in, const void* nmap, int W) {
+  static const int off = [] { const char* e = getenv("BSVD_B200_NO_RAW_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  return !off && (W % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)nmap % 16 == 0);
 }
 
 // Packed weights as a 2-D tensor [rows][64] (rows of 128 B, already swizzled by the host): the CTA-pair
@@ -363,7 +385,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
   static const int tma_shift_on = [] { const char* e = getenv("BSVD_B200_TMA_SHIFT"); return e ? atoi(e) : 0; }();   // measured: -3 % when on
   const bool tma_out = tma_on && cta2 && (!s.shift || (tma_shift_on && !s.pixshuf)) &&
-                       !(s.skip && !skip_mma) && !s.first_im2col &&
+                       !(s.skip && !skip_mma) && !s.first_im2col && s.stride == 1 &&
                        !s.final_out && !(desc_variant & ~(2 | 4 | 16 | 128));
   // two staging tiles per warp when they fit; the stacked 64->64 stages (resident 72 KB bank) have
   // room for one, whose TMA read is awaited right before it is rewritten
@@ -394,6 +416,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
                      CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     p.tma_out = 1; p.stg_bytes_per_warp = 2 * kStageBytesPerWarp;
     L->map = L->map_o; L->map_w = L->map_o; L->map_s = L->map_o;
+    L->map_raw = L->map_o; L->map_rawnm = L->map_o; L->first_raw_tma = 0;   // set per call (input pointer)
     L->grid = std::min(p.total_tiles, num_sms());
     L->smem = kFirstSmem;
     L->ntile = -1; L->rows = kFirstR;
@@ -428,6 +451,9 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (stacked) { p.w_stage_bytes = 192u * 128u; p.w_rows_cta = 192; }
   const size_t budget = kSmemOptIn - 1024 - kStagingBytes;   // minus alignment slack and staging
   if (stacked) p.mode = 2;
+  // stride 2: sub-plane boxes (conv_tc.cuh PIPE 4) unless BSVD_B200_S2_TAPS=1 asks for the per-tap boxes
+  static const int s2_taps = [] { const char* e = getenv("BSVD_B200_S2_TAPS"); return (e && e[0] == '1') ? 1 : 0; }();
+  const bool s2_boxes = p.mode == 1 && cta2 && !s2_taps && !desc_variant;
   if (p.mode != 1) {
     p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
     p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
@@ -442,6 +468,16 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
       p.w_stages = (int)std::min<size_t>(kMaxStages, left / p.w_stage_bytes);
       if (p.w_stages < 2) return fail("shared memory budget too small for weight stages");
     }
+  } else if (s2_boxes) {
+    // one box per input sub-plane: ring slots sized for the largest, (R+1) rows x 129 px
+    p.mode = 4;
+    p.a_tx_bytes = (uint32_t)(s.rows + 1) * kS2BoxPx * 128u;
+    p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
+    p.a_stages = 3;
+    const size_t left = budget - (size_t)p.a_stages * p.a_stage_bytes;
+    p.w_stages = (int)std::min<size_t>(kMaxStages, left / p.w_stage_bytes);
+    p.w_resident = 0;
+    if (p.w_stages < 3) return fail("shared memory budget too small for stride-2 stages");
   } else {
     p.a_tx_bytes = (uint32_t)s.rows * kRunPx * 128u;
     p.a_stage_bytes = p.a_tx_bytes;
@@ -484,8 +520,9 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
 
   const int cin_map = s.first_im2col ? kChunk : s.cin;
-  int rc = (p.mode != 1) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
-                         : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
+  int rc = (s.stride != 2) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
+           : (p.mode == 4) ? make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows + 1, kS2BoxPx)
+                           : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
   if (rc) return rc;
   if (cta2) {
     rc = make_map_w(&L->map_w, sd.wpack, s.pack_elems() / kChunk, p.w_rows_cta);
@@ -494,6 +531,10 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     L->map_w = L->map;   // unused
   }
   L->map_s = L->map; L->map_o = L->map;   // unused unless set below
+  if (p.mode == 4) {   // even input rows: R-row boxes (the skip map slot is free: stride-2 stages have no skip)
+    rc = make_map_s2(&L->map_s, io.in, io.T, io.H, io.W, cin_map, s.rows, kS2BoxPx);
+    if (rc) return rc;
+  }
   const long long frame_bytes = p.out_frame_stride * 2;
   if (skip_mma) {
     if (p.w_stage_bytes != 16384u || p.w_resident || s.cin_chunks * s.ntaps() < 4 * (s.ntile / 64))
@@ -520,31 +561,32 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
-    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
-    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
-    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
     attr_done[dev & 63] = true;
   }
   if (!L.first_in) return fail("first stage launched without an input pointer");
+  const bool raw = L.first_raw_tma && !L.first_u8;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(kFirstThreads);
-  cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+  cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(raw ? kFirstThreadsRaw : kFirstThreads);
+  cfg.dynamicSmemBytes = raw ? kFirstSmemRaw : L.smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  float* no_norm = nullptr;
-  if (L.first_u8) {
-    if (L.p.flags & EPI_BF16)
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true, true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, L.first_norm));
-    else
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false, true>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, L.first_norm));
-  } else if (L.p.flags & EPI_BF16)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<true, false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, no_norm));
-  else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<false, false>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, no_norm));
+  float* norm = L.first_u8 ? L.first_norm : nullptr;
+  const bool bf = (L.p.flags & EPI_BF16) != 0;
+#define BSVD_FIRST(B, U, R) \
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<B, U, R>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, norm, L.map_raw, L.map_rawnm))
+  if (raw) { if (bf) BSVD_FIRST(true, false, true); else BSVD_FIRST(false, false, true); }
+  else if (L.first_u8) { if (bf) BSVD_FIRST(true, true, false); else BSVD_FIRST(false, true, false); }
+  else { if (bf) BSVD_FIRST(true, false, false); else BSVD_FIRST(false, false, false); }
+#undef BSVD_FIRST
   return 0;
 }
 
@@ -657,6 +699,8 @@ struct bsvd_handle {
   struct StreamLayer {
     StageLaunch tmpl;                 // planned for T=1 on ring slot 0
     std::vector<CUtensorMap> maps;    // one per input ring slot
+    std::vector<CUtensorMap> maps2;   // stride-2 sub-plane pipeline: the second (R-row) box map per slot
+    std::vector<CUtensorMap> raw_maps;   // first conv: one raw-plane map per raw ring slot
   };
   struct Stream {
     int H = 0, W = 0;
@@ -670,6 +714,13 @@ struct bsvd_handle {
     float* raw = nullptr;             // fp32 [9][4][H][W] ring of the raw network input
     uint8_t* aux = nullptr;           // 16-bit [9][H][W][4] ring: temp1 output channels 0..3 (skip1 of temp2)
     StreamLayer layers[BSVD_NUM_LAYERS];
+    // steady-state pushes replay one CUDA graph per ring phase (all ring sizes divide kPhases)
+    static constexpr int kPhases = 45;          // lcm(1, 3, 5, 9)
+    cudaGraphExec_t gexec[kPhases] = {};
+    unsigned long long gepoch = 0;              // weights_epoch the graphs were captured with
+    cudaStream_t cap = nullptr;                 // capture stream (the caller's may be the legacy stream)
+    float* out_slot = nullptr;                  // [3][H][W] fp32: where a replayed graph leaves its frame
+    long long graph_replays = 0;
   } stream;
 };
 
@@ -1008,6 +1059,16 @@ static int forward_clip_impl(bsvd_handle* h, const float* in, const float* noise
   // stage 0 (input staging) is fused into temp1.inc.convblock.0 (first_conv.cuh)
   h->plan[0].first_in = in; h->plan[0].first_nmap = noise_map; h->plan[0].first_inc = in_c;
   h->plan[0].first_u8 = o.u8_io; h->plan[0].first_norm = o.u8_io ? h->d_norm : nullptr;
+  {
+    // raw fp32 planes through TMA unless the caller view is reflect-padded / uint8 / misaligned
+    StageLaunch& L0 = h->plan[0];
+    const bool same_view = (!o.src_H || o.src_H == H) && (!o.src_W || o.src_W == W);
+    L0.first_raw_tma = (!o.u8_io && !o.use_sigma && same_view && raw_tma_ok(in, noise_map, W)) ? 1 : 0;
+    if (L0.first_raw_tma) {
+      if (make_map_raw(&L0.map_raw, in, (long long)T * in_c, H, W, in_c)) return 1;
+      if (noise_map && make_map_raw(&L0.map_rawnm, noise_map, T, H, W, 1)) return 1;
+    }
+  }
   if (evs) CUDA_TRY(cudaEventRecord((*evs)[1], st));
   int launches = 0;
   h->plan[15].p.resid_in = o.u8_io ? h->d_norm : in;   // temp1 residual reads the raw input (skip1)
@@ -1129,6 +1190,32 @@ int bsvd_psnr(const float* a, const float* b, int T, int C, int H, int W, int cr
   return 0;
 }
 
+// ---- SSIM per frame (calculate_ssim, BasicSR/basicsr/metrics/psnr_ssim.py:49-128) ------------------------
+int bsvd_ssim(const float* a, const float* b, int T, int C, int H, int W, int crop_border, float data_range,
+              float* ssim, void* stream) {
+  if (!a || !b || !ssim) return fail("null argument");
+  const int hh = H - 2 * crop_border, ww = W - 2 * crop_border;
+  if (T < 1 || C < 1 || crop_border < 0 || hh < kSsimWin || ww < kSsimWin || !(data_range > 0.f))
+    return fail("bad SSIM arguments T=%d C=%d %dx%d crop_border=%d data_range=%g (the cropped image must hold an "
+                "11x11 window)", T, C, H, W, crop_border, (double)data_range);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int oh = hh - (kSsimWin - 1), ow = ww - (kSsimWin - 1);
+  const int tiles_x = (ow + kSsimTile - 1) / kSsimTile, tiles_y = (oh + kSsimTile - 1) / kSsimTile;
+  SsimWindow g;   // cv2.getGaussianKernel(11, 1.5): exp(-(i - 5)^2 / (2 sigma^2)), normalised
+  double sum = 0.0;
+  for (int i = 0; i < kSsimWin; ++i) { g.w[i] = exp(-((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); sum += g.w[i]; }
+  for (int i = 0; i < kSsimWin; ++i) g.w[i] /= sum;
+  double* part = nullptr;
+  const size_t n_per_frame = (size_t)C * tiles_x * tiles_y;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(double) * T * n_per_frame, st));
+  ssim_partial_kernel<<<dim3(tiles_x * tiles_y, C, T), kSsimTile * kSsimTile, 0, st>>>(
+      a, b, C, H, W, crop_border, (double)data_range, g, tiles_x, tiles_y, part);
+  ssim_final_kernel<<<T, 256, 0, st>>>(part, (int)n_per_frame, (double)C * oh * ow, ssim);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(part, st));
+  return 0;
+}
+
 static int ensure_dev(float** p, size_t* cur, size_t need) {
   if (*cur >= need) return 0;
   if (*p) cudaFree(*p);
@@ -1220,8 +1307,14 @@ int bsvd_host_sync(bsvd_handle* h) {
   return 0;
 }
 
+static void drop_stream_graphs(bsvd_handle* h) {
+  for (auto& g : h->stream.gexec)
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
 static void free_stream(bsvd_handle* h) {
   auto& S = h->stream;
+  drop_stream_graphs(h);
+  if (S.cap) cudaStreamDestroy(S.cap);
   if (S.ws) cudaFree(S.ws);
   S = bsvd_handle::Stream();
 }
@@ -1244,11 +1337,14 @@ static int build_stream(bsvd_handle* h, int H, int W) {
   total += raw_bytes;
   const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
   total += 9 * aux_slot;
+  const size_t out_bytes = align_up((size_t)3 * H * W * sizeof(float), 1024);
+  total += out_bytes;
   CUDA_TRY(cudaMalloc(&S.ws, total));
   S.ws_bytes = total;
   uint8_t* p = reinterpret_cast<uint8_t*>(S.ws);
   S.raw = reinterpret_cast<float*>(p); p += raw_bytes;
   S.aux = p; p += 9 * aux_slot;
+  S.out_slot = reinterpret_cast<float*>(p); p += out_bytes;
   for (int b = 0; b < 2; ++b)
     for (int k = 0; k < kNumRings; ++k) { S.ring[b][k] = p; p += ring_slot_bytes(h, k, H, W) * kRingSlots[k]; }
   for (int b = 0; b < 2; ++b)
@@ -1282,13 +1378,79 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       const int nslots = kRingSlots[in_ring];
       SL.maps.resize(nslots);
       const int cin_map = sd.spec.first_im2col ? kChunk : sd.spec.cin;
+      if (b == 0 && l == 0 && raw_tma_ok(S.raw, nullptr, W)) {
+        SL.raw_maps.resize(9);
+        for (int k = 0; k < 9; ++k)
+          if (make_map_raw(&SL.raw_maps[k], S.raw + (size_t)k * 4 * H * W, h->cfg.in_ch, H, W, h->cfg.in_ch)) return 1;
+      }
+      const bool s2b = SL.tmpl.p.mode == 4;
+      if (s2b) SL.maps2.resize(nslots);
       for (int k = 0; k < nslots; ++k) {
         const void* base = S.ring[in_blk][in_ring] + (size_t)k * in_bytes;
-        int rc = (sd.spec.stride == 2) ? make_map_s2(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows)
-                                       : make_map_halo(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows);
+        int rc = (sd.spec.stride != 2) ? make_map_halo(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows)
+                 : s2b ? make_map_s2(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows + 1, kS2BoxPx)
+                       : make_map_s2(&SL.maps[k], base, 1, io.H, io.W, cin_map, sd.spec.rows);
+        if (!rc && s2b) rc = make_map_s2(&SL.maps2[k], base, 1, io.H, io.W, cin_map, sd.spec.rows, kS2BoxPx);
         if (rc) return rc;
       }
     }
+  return 0;
+}
+
+// The stage launches of one push (step s, F frames known): every stage whose delayed frame exists runs
+// on one frame; ring slots are selected by frame index.  `st` may be a capturing stream.
+static int run_stream_layers(bsvd_handle* h, long long s, long long F, cudaStream_t st, float* out,
+                             int* produced, int* launches_out) {
+  auto& S = h->stream;
+  const int H = S.H, W = S.W;
+  const size_t plane = (size_t)H * W;
+  int launches = 0;
+  for (int b = 0; b < 2; ++b)
+    for (int l = 0; l < 16; ++l) {
+      const long long f = s - (kLayerDelay[l] + b * kBlockDelay);
+      if (f < 0 || f >= F) continue;   // None propagation (bsvd_arch.py:135,139,219-224,...)
+      auto& SL = S.layers[b * 16 + l];
+      StageLaunch L = SL.tmpl;
+      const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
+      L.map = SL.maps[f % kRingSlots[in_ring]];
+      if (!SL.maps2.empty()) L.map_s = SL.maps2[f % kRingSlots[in_ring]];
+      const int oring = kLayerOut[l];
+      const size_t ob = ring_slot_bytes(h, oring, H, W);
+      auto oslot = [&](long long ff) { return S.ring[b][oring] + (size_t)(ff % kRingSlots[oring]) * ob; };
+      ConvParams& p = L.p;
+      p.out = oslot(f);
+      if (p.flags & EPI_SHIFT) {
+        p.out_prev = (f > 0) ? oslot(f - 1) : nullptr;
+        p.out_next = oslot(f + 1);
+      }
+      p.out_t0 = (int)(f % kRingSlots[oring]);     // TMA stores address the ring through map_o
+      if (l == 10) {
+        p.skip_t0 = (int)(f % kRingSlots[kRingX1]);   // skip add on the tensor core: ring slot of map_s
+        p.skip = S.ring[b][kRingX1] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX1, H, W);
+      }
+      if (l == 13) {
+        p.skip_t0 = (int)(f % kRingSlots[kRingX0]);
+        p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX0, H, W);
+      }
+      const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+      if (l == 0 && b == 0) {
+        L.first_in = S.raw + (size_t)(f % 9) * 4 * plane;   // raw ring slot holds all 4 channels
+        L.first_nmap = nullptr; L.first_inc = h->cfg.in_ch;   // blind model: planes 0..2 only
+        if (!SL.raw_maps.empty()) { L.first_raw_tma = 1; L.map_raw = SL.raw_maps[f % 9]; }
+      }
+      if (l == 15 && b == 0) {
+        p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
+        p.aux_out = S.aux + (size_t)(f % 9) * aux_slot;
+      }
+      if (l == 15 && b == 1) {
+        p.skip = S.aux + (size_t)(f % 9) * aux_slot;
+        p.out = out;
+        if (produced) *produced = 1;
+      }
+      if (launch_stage(L, st)) return 1;
+      ++launches;
+    }
+  if (launches_out) *launches_out = launches;
   return 0;
 }
 
@@ -1325,53 +1487,45 @@ int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map,
     S.ended = true;
   }
   const long long F = S.n_in;          // frames known so far; final once ended
-  for (int b = 0; b < 2; ++b)
-    for (int l = 0; l < 16; ++l) {
-      const long long f = s - (kLayerDelay[l] + b * kBlockDelay);
-      if (f < 0 || f >= F) continue;   // None propagation (bsvd_arch.py:135,139,219-224,...)
-      auto& SL = S.layers[b * 16 + l];
-      StageLaunch L = SL.tmpl;
-      const int in_ring = (b == 1 && l == 0) ? kRingM : kLayerIn[l];
-      L.map = SL.maps[f % kRingSlots[in_ring]];
-      const int oring = kLayerOut[l];
-      const size_t ob = ring_slot_bytes(h, oring, H, W);
-      auto oslot = [&](long long ff) { return S.ring[b][oring] + (size_t)(ff % kRingSlots[oring]) * ob; };
-      ConvParams& p = L.p;
-      p.out = oslot(f);
-      if (p.flags & EPI_SHIFT) {
-        p.out_prev = (f > 0) ? oslot(f - 1) : nullptr;
-        p.out_next = oslot(f + 1);
+  // Steady state (every one of the 32 stages has a frame to work on): the launches of one push depend
+  // only on the ring phase s mod 45, so they are captured once per phase into a CUDA graph and replayed —
+  // one submission instead of 32 cudaLaunchKernelEx calls (the PDL edges between the stages are kept).
+  // The graph leaves its frame in an internal slot; a D2D copy hands it to the caller's buffer.
+  static const int graphs_on = [] { const char* e = getenv("BSVD_B200_NO_STREAM_GRAPH"); return (e && e[0] == '1') ? 0 : 1; }();
+  const bool steady = frame && s > 2 * kBlockDelay;   // every stage has run once through the plain path
+  if (steady && graphs_on) {
+    if (S.gepoch != h->weights_epoch) { drop_stream_graphs(h); S.gepoch = h->weights_epoch; }
+    const int ph = (int)(s % bsvd_handle::Stream::kPhases);
+    if (!S.gexec[ph]) {
+      if (!S.cap) CUDA_TRY(cudaStreamCreateWithFlags(&S.cap, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamBeginCapture(S.cap, cudaStreamCaptureModeThreadLocal));
+      int n = 0, prod = 0;
+      const int rc = run_stream_layers(h, s, F, S.cap, S.out_slot, &prod, &n);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(S.cap, &g);
+      if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc ? 1 : fail("capturing the streaming step failed: %s", cudaGetErrorString(e));
       }
-      p.out_t0 = (int)(f % kRingSlots[oring]);     // TMA stores address the ring through map_o
-      if (l == 10) {
-        p.skip_t0 = (int)(f % kRingSlots[kRingX1]);   // skip add on the tensor core: ring slot of map_s
-        p.skip = S.ring[b][kRingX1] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX1, H, W);
-      }
-      if (l == 13) {
-        p.skip_t0 = (int)(f % kRingSlots[kRingX0]);
-        p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX0, H, W);
-      }
-      const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
-      if (l == 0 && b == 0) {
-        L.first_in = S.raw + (size_t)(f % 9) * 4 * plane;   // raw ring slot holds all 4 channels
-        L.first_nmap = nullptr; L.first_inc = h->cfg.in_ch;   // blind model: planes 0..2 only
-      }
-      if (l == 15 && b == 0) {
-        p.resid_in = S.raw + (size_t)(f % 9) * 4 * plane;
-        p.aux_out = S.aux + (size_t)(f % 9) * aux_slot;
-      }
-      if (l == 15 && b == 1) {
-        p.skip = S.aux + (size_t)(f % 9) * aux_slot;
-        p.out = out;
-        if (produced) *produced = 1;
-      }
-      if (launch_stage(L, st)) return 1;
-      ++launches;
+      const cudaError_t ei = cudaGraphInstantiate(&S.gexec[ph], g, 0);
+      cudaGraphDestroy(g);
+      if (ei != cudaSuccess) { S.gexec[ph] = nullptr; return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
     }
+    CUDA_TRY(cudaGraphLaunch(S.gexec[ph], st));
+    CUDA_TRY(cudaMemcpyAsync(out, S.out_slot, (size_t)3 * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ++S.graph_replays;
+    launches = BSVD_NUM_LAYERS;
+    if (produced) *produced = 1;
+  } else {
+    if (run_stream_layers(h, s, F, st, out, produced, &launches)) return 1;
+  }
   ++S.step;
   h->last_launches = launches;
   return 0;
 }
+
+long long bsvd_stream_graph_replays(const bsvd_handle* h) { return h ? h->stream.graph_replays : 0; }
 
 int bsvd_reset(bsvd_handle* h) {
   if (!h) return fail("null handle");

@@ -36,6 +36,10 @@
 
 #include <type_traits>
 
+// the PIPE == 4 branches leave their tile loops with `continue`: the generic loops behind them are
+// unreachable in those instances by design
+#pragma nv_diag_suppress 128
+
 namespace bsvd {
 
 constexpr int kRunPx = 128;        // pixels per MMA row-run (UMMA M)
@@ -47,6 +51,18 @@ constexpr int kThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilo
 constexpr int kEpiThreads = 256;
 constexpr int kStageBytesPerWarp = 2048;   // epilogue staging: [32 px][32 ch] 16-bit per warp
 constexpr int kMaxBias = 512;
+// Stride-2 stages (PIPE 4): the 3x3 taps of a stride-2 conv touch only four sub-planes (row parity py,
+// column parity px) of the input.  One TMA box per sub-plane from the space-to-depth view
+// [T][H/2][2][W/2][2C], consumed by the taps that read it in the order below (tap = dy*3+dx):
+//   box 0 (py1,px1): taps 0,2,6,8   box 1 (py1,px0): taps 1,7   box 2 (py0,px1): taps 3,5   box 3 (py0,px0): tap 4
+// A tap's operand is its box offset by (row, col) 128-byte pixels, exactly like the halo tile.
+constexpr int kS2BoxPx = kRunPx + 1;                       // 129 pixels per box row
+__host__ __device__ constexpr int s2_tap(int j) {           // j-th tap in consumption order
+  return j == 0 ? 0 : j == 1 ? 2 : j == 2 ? 6 : j == 3 ? 8 : j == 4 ? 1 : j == 5 ? 7 : j == 6 ? 3 : j == 7 ? 5 : 4;
+}
+__host__ __device__ constexpr int s2_box(int j) { return j < 4 ? 0 : j < 6 ? 1 : j < 8 ? 2 : 3; }
+__host__ __device__ constexpr bool s2_box_first(int j) { return j == 0 || s2_box(j) != s2_box(j - 1); }
+__host__ __device__ constexpr bool s2_box_last(int j) { return j == 8 || s2_box(j) != s2_box(j + 1); }
 
 // masks of epilogue features a kernel instance is compiled with
 enum : int {
@@ -71,8 +87,9 @@ struct ConvParams {
   int xblocks, yblocks; // ceil(W/128), ceil(H/R)
   int total_tiles;      // 1-CTA: positions*n_tiles; CTA pair: ceil(positions/2)*n_tiles
   int positions;        // T*yblocks*xblocks pixel tiles
-  int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2),
-                        // 2 = halo with the vertical taps stacked in N (64->64 stages, see below)
+  int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2, generic pipeline only),
+                        // 2 = halo with the vertical taps stacked in N (64->64 stages, see below),
+                        // 4 = stride 2 with one box per input sub-plane (see s2_tap)
   int w_rows_cta;       // CTA pair: filter rows one CTA stages per W stage
   int cin_total;        // Cin (stride-2 coordinate math)
   // ---- pipeline ----
@@ -751,8 +768,9 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 // The kernel
 // --------------------------------------------------------------------------------------------
 // PIPE: compile-time pipeline shape, so the producer / MMA loops carry no per-tap parameter tests:
-//   0 halo tile + streamed filter slabs   1 stride-2 per-tap boxes + streamed slabs
+//   0 halo tile + streamed filter slabs   1 stride-2 per-tap boxes + streamed slabs (generic only)
 //   2 stacked 64->64 (resident bank)      3 generic: mode / w_resident read from ConvParams
+//   4 stride-2 sub-plane boxes + streamed slabs (map_s = the R-row box map of the even input rows)
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -880,6 +898,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = tile0; tile < pp.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
         int nskip = 0;
+        if constexpr (PIPE == 4 && CTA2) {
+          // stride 2, sub-plane boxes: 4 A boxes + 9 filter slabs per chunk, issued in consumption order
+          for (int c = 0; c < pp.cin_chunks; ++c) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              if (s2_box_first(j)) {
+                const int b = s2_box(j);
+                const int py = (b < 2) ? 1 : 0, px = (b == 0 || b == 2) ? 1 : 0;
+                const uint32_t bytes = static_cast<uint32_t>((py ? R + 1 : R) * kS2BoxPx * 128);
+                mbar_wait(a_empty(sa), pa ^ 1);
+                if (rank == 0) mbar_expect_tx(a_full(sa), 2 * bytes);
+                tma_load_5d_2sm(a_base + sa * pp.a_stage_bytes, py ? &map_a : &map_s, a_full(sa),
+                                px * pp.cin_total + c * kChunk, px ? tc.x0 - 1 : tc.x0, py,
+                                py ? tc.y0 - 1 : tc.y0, tc.t);
+                if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
+              }
+              mbar_wait(w_empty(sw), pw ^ 1);
+              if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
+              const size_t blk = static_cast<size_t>(tc.nt * pp.cin_chunks + c) * 9 + s2_tap(j);
+              tma_load_2d_2sm(w_base + sw * pp.w_stage_bytes, &map_w, w_full(sw), 0,
+                              (static_cast<int>(blk) * 2 + static_cast<int>(rank)) * pp.w_rows_cta);
+              if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int c = 0; c < pp.cin_chunks; ++c) {
           if (pp.mode != 1) {
             mbar_wait(a_empty(sa), pa ^ 1);
@@ -1024,6 +1068,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kAccCols;
         int nskip = 0;
+        if constexpr (PIPE == 4 && CTA2) {
+          for (int c = 0; c < pp.cin_chunks; ++c) {
+            uint32_t a_lo0 = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              if (s2_box_first(j)) {
+                mbar_wait(a_full(sa), pa);
+                a_lo0 = a_lo_base + sa * a_lo_step;
+              }
+              mbar_wait(w_full(sw), pw);
+              tc_fence_after();
+              const int tap = s2_tap(j);
+              const int dy = tap / 3, dx = tap % 3;
+              const int ro = (dy == 2) ? 1 : 0, co = (dx == 2) ? 1 : 0;     // offset inside the sub-plane box
+              const uint32_t b_lo0 = w_lo_base + sw * w_lo_step;
+              const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
+              if (leader) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const uint32_t a_off = static_cast<uint32_t>(((r + ro) * kS2BoxPx + co) * 8);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(tmem_acc + r * NTILE, desc_hi | (a_lo0 + a_off + k * 2u), desc_hi | (b_lo0 + k * 2u),
+                                 idesc, (k > 0) ? 1u : first);
+                }
+                umma_commit_2sm(w_empty(sw));
+                if (s2_box_last(j)) umma_commit_2sm(a_empty(sa));
+              }
+              __syncwarp();
+              if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
+              if (s2_box_last(j)) {
+                if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
+              }
+            }
+          }
+          if (leader) umma_commit_2sm(acc_full(buf));
+          __syncwarp();
+          continue;
+        }
         for (int c = 0; c < pp.cin_chunks; ++c) {
           if (pp.mode == 0 && !dbg_no_load) {
             mbar_wait(a_full(sa), pa);

@@ -9,6 +9,12 @@
 //              map) -> 16-bit swizzled rows, fence.proxy.async
 //   warp  8    MMA issuer (8 MMAs per 2-row tile, filter bank resident)
 //   warps 9-16 epilogue (shared with conv_tc.cuh: bias, ReLU6, staged coalesced NHWC stores)
+//   warp  17   RAW instances only: TMA loader of the raw fp32 tiles
+// RAW = true (plain fp32 NCHW input, no reflection): the haloed raw tile [4 planes][4 rows][132 px] of
+// every tile is fetched by TMA into a 6-deep shared-memory ring, several tiles ahead (out-of-bounds = the
+// conv's zero padding), and the producers read their 48 values with conflict-free LDS.  With direct global
+// loads (RAW = false: uint8 / reflect-padded callers) each producer thread sits on 48 scalar LDGs of DRAM
+// latency per tile with only two tiles in flight per SM — measured 0.40 of the HBM roofline.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -22,21 +28,37 @@ constexpr uint32_t kFirstAStage = kFirstR * kRunPx * 128;   // 32 KB
 constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
 // epilogue staging: two 2 KB tiles per warp (units leave through TMA stores, see conv_tc.cuh)
 constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * 2 * kStageBytesPerWarp;
+// raw-tile ring of the RAW instances
+constexpr int kRawStages = 6;
+constexpr int kRawPx = 132;                                  // 130 needed; 132 * 4 B is a multiple of 16 B
+constexpr int kRawRows = kFirstR + 2;
+constexpr uint32_t kRawPlane = kRawRows * kRawPx * 4;        // 2112 B
+constexpr uint32_t kRawStage = 4 * kRawPlane;                // 8448 B (4 channel planes)
+constexpr size_t kFirstSmemRaw = kFirstSmem + kRawStages * kRawStage;
+constexpr int kFirstThreadsRaw = kFirstThreads + 32;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 // U8: the raw input is uint8 [T][H][W][3] (decoded frames, HWC; ConvParams::u8_bgr = channel order
 // B,G,R as cv2 delivers them): normalised with /255 on the fly (img2tensor,
 // BasicSR/basicsr/utils/img_util.py), and the normalised RGB planes of every pixel are also written
 // to `norm_out` (fp32 [T][3][H][W]) for the temp1 residual, which needs the raw input again.
-template <bool BF16, bool U8 = false>
-__global__ void __launch_bounds__(kFirstThreads, 1)
+template <bool BF16, bool U8 = false, bool RAW = false>
+__global__ void __launch_bounds__(RAW ? kFirstThreadsRaw : kFirstThreads, 1)
 first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, int in_c,
                   const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p,
-                  float* __restrict__ norm_out = nullptr) {
+                  float* __restrict__ norm_out, const __grid_constant__ CUtensorMap map_raw,
+                  const __grid_constant__ CUtensorMap map_rawnm) {
+  static_assert(!(U8 && RAW), "the raw-tile TMA path takes fp32 planes");
   constexpr int NT = 64;
   constexpr int kAccCols = kFirstR * NT;
   constexpr int kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kFirstStages + 5];
+  __shared__ __align__(8) uint64_t bars[2 * kFirstStages + 5 + 2 * kRawStages];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -50,6 +72,10 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   auto acc_full = [&](int b) { return bar0 + 8u * (2 * kFirstStages + b); };
   auto acc_empty = [&](int b) { return bar0 + 8u * (2 * kFirstStages + 2 + b); };
   const uint32_t w_full = bar0 + 8u * (2 * kFirstStages + 4);
+  auto raw_full = [&](int s) { return bar0 + 8u * (2 * kFirstStages + 5 + s); };
+  auto raw_empty = [&](int s) { return bar0 + 8u * (2 * kFirstStages + 5 + kRawStages + s); };
+  const uint32_t raw_base = stg_base + 8 * 2 * kStageBytesPerWarp;
+  constexpr int kNumThreads = RAW ? kFirstThreadsRaw : kFirstThreads;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFirstStages; ++s) {
@@ -61,11 +87,22 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       mbar_init(acc_empty(b), 8);
     }
     mbar_init(w_full, 1);
+    if constexpr (RAW) {
+      for (int s = 0; s < kRawStages; ++s) {
+        mbar_init(raw_full(s), 1);
+        mbar_init(raw_empty(s), kFirstProducers);
+      }
+    }
     fence_barrier_init();
   }
   // K slots 36..63 of every patch row are zero for the whole kernel: clear the stages once
-  for (uint32_t off = threadIdx.x * 16; off < kFirstStages * kFirstAStage; off += kFirstThreads * 16)
+  for (uint32_t off = threadIdx.x * 16; off < kFirstStages * kFirstAStage; off += kNumThreads * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + off), "r"(0) : "memory");
+  if constexpr (RAW) {
+    // a channel plane no TMA box ever fills (blind 3-channel input) must read as zero, not as garbage
+    for (uint32_t off = threadIdx.x * 16; off < kRawStages * kRawStage; off += kNumThreads * 16)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(raw_base + off), "r"(0) : "memory");
+  }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
@@ -118,6 +155,23 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         pc[c] = (c < in_c) ? in + (static_cast<long long>(tc.t) * in_c + c) * plane
                            : (nmap && c == in_c ? nmap + static_cast<long long>(tc.t) * plane : nullptr);
       const float fill = p.use_sigma ? p.sigma_const : 0.f;      // constant noise map (inside the image)
+      if constexpr (RAW) {
+        // the loader warp's TMA box [4 planes][4 rows][132 px] starts at (x0 - 1, y0 - 1): zero outside
+        const uint32_t rs = it % kRawStages, rp = (it / kRawStages) & 1;
+        mbar_wait(raw_full(rs), rp);
+        const uint32_t src = raw_base + rs * kRawStage + i * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              uint32_t u;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(src + c * kRawPlane + (rr * kRawPx + dx) * 4) : "memory");
+              v[rr][dx][c] = __uint_as_float(u);
+            }
+        mbar_arrive_release(raw_empty(rs));
+      } else {
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
@@ -140,6 +194,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
             }
           }
         }
+      }
       }
       if constexpr (U8) {
         // this thread's own two pixels (rows y0, y0+1 at column x): normalised RGB for the residual
@@ -180,6 +235,22 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       }
       fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive_release(a_full(sa));
+    }
+  } else if (RAW && warp == 17) {
+    // ===================================== raw-tile loader =====================================
+    if (lane == 0) {
+      const int nm_planes = (nmap != nullptr) ? 1 : 0;
+      const uint32_t tx = static_cast<uint32_t>(in_c + nm_planes) * kRawPlane;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t rs = it % kRawStages, rp = (it / kRawStages) & 1;
+        const TileCoord tc = decode_tile<kFirstR>(p, tile);
+        mbar_wait(raw_empty(rs), rp ^ 1);
+        mbar_expect_tx(raw_full(rs), tx);
+        const uint32_t dst = raw_base + rs * kRawStage;
+        tma_load_3d(dst, &map_raw, raw_full(rs), tc.x0 - 1, tc.y0 - 1, tc.t * in_c);
+        if (nm_planes) tma_load_3d(dst + in_c * kRawPlane, &map_rawnm, raw_full(rs), tc.x0 - 1, tc.y0 - 1, tc.t);
+      }
     }
   } else if (warp == 8) {
     // ====================================== MMA issuer ======================================

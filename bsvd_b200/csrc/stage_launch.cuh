@@ -40,6 +40,9 @@ struct StageLaunch {
   int first_inc = 4;
   int first_u8 = 0;               // raw input is uint8 HWC (bsvd_denoise_clip_u8)
   float* first_norm = nullptr;    // fp32 [T][3][H][W] copy of the normalised frames (temp1 residual)
+  // raw fp32 planes through TMA (first_conv.cuh RAW instances): [planes][H][W] views of the input / noise map
+  int first_raw_tma = 0;
+  CUtensorMap map_raw, map_rawnm;
 };
 
 // pick the compile-time pipeline shape (conv_tc.cuh PIPE) the plan asks for
@@ -47,14 +50,18 @@ template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW>
 static int launch_inst(const StageLaunch& L, cudaStream_t st) {
   if constexpr (CTA2) {
     const int mode = L.p.mode, res = L.p.w_resident;
+    if (mode == 4) {
+      // stride 2 with sub-plane boxes: only this pipeline implements it
+      if constexpr ((MASK & (EPI_PIXSHUF | EPI_RESID_IN | EPI_TMA_OUT)) == 0)
+        return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 4>(L, st);
+      return fail("no stride-2 kernel instance for this stage (NTILE=%d R=%d)", NTILE, R);
+    }
     if (L.p.desc_variant != 0 || L.p.tap_begin != 0 || L.p.tap_end != (mode == 2 ? 3 : 9)) {
       // debug switches / partial tap ranges only exist in the generic pipeline
     } else if constexpr (NTILE == 64 && R == 2) {
       if (mode == 2 && res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 2>(L, st);
     } else {
       if (mode == 0 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 0>(L, st);
-      if constexpr ((MASK & (EPI_PIXSHUF | EPI_RESID_IN)) == 0)
-        if (mode == 1 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 1>(L, st);
     }
   }
   return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 3>(L, st);

@@ -9,7 +9,7 @@
 noise map are synthesised by the first kernel's loads, clamp and crop by the last kernel's stores.
 `denoise_sequence_unfused` keeps the same steps as separate torch ops (the reference's structure);
 the tests check the two against each other.  `psnr_per_frame` is calculate_psnr_float
-(BasicSR/basicsr/metrics/psnr_ssim.py:130-168) on the device.
+(BasicSR/basicsr/metrics/psnr_ssim.py:130-168) and `ssim_per_frame` calculate_ssim (:49-128) on the device.
 """
 from __future__ import annotations
 
@@ -52,6 +52,22 @@ def psnr_per_frame(a: torch.Tensor, b: torch.Tensor, crop_border: int = 0) -> to
     with torch.cuda.device(a.device):
         capi.check(capi.load_library().bsvd_psnr(
             a.data_ptr(), b.data_ptr(), Fr, C, H, W, crop_border, out.data_ptr(),
+            torch.cuda.current_stream(a.device).cuda_stream))
+    return out
+
+
+def ssim_per_frame(a: torch.Tensor, b: torch.Tensor, crop_border: int = 0, data_range: float = 1.0) -> torch.Tensor:
+    """[F,C,H,W] x2 -> [F] SSIM on the device (bsvd_ssim): calculate_ssim
+    (BasicSR/basicsr/metrics/psnr_ssim.py:49-128) per frame.  data_range 1 for [0,1] floats, 255 for the
+    reference's [0,255] images (e.g. uint8 frames converted with .float())."""
+    from . import capi
+    assert a.shape == b.shape and a.is_cuda and b.is_cuda
+    a = a.float().contiguous(); b = b.float().contiguous()
+    Fr, C, H, W = a.shape
+    out = torch.empty(Fr, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        capi.check(capi.load_library().bsvd_ssim(
+            a.data_ptr(), b.data_ptr(), Fr, C, H, W, crop_border, float(data_range), out.data_ptr(),
             torch.cuda.current_stream(a.device).cuda_stream))
     return out
 

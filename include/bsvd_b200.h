@@ -120,6 +120,15 @@ int bsvd_denoise_clip_u8(bsvd_handle* h, const uint8_t* in, float sigma, uint8_t
 int bsvd_psnr(const float* a, const float* b, int T, int C, int H, int W, int crop_border,
               float* psnr, void* stream);
 
+/* -- on-device SSIM ----------------------------------------------------------------
+ * replaces calculate_ssim (BasicSR/basicsr/metrics/psnr_ssim.py:49-128) applied per frame: 11x11 Gaussian
+ * window (sigma 1.5) at every position where it fits inside the crop_border-cropped image, the five local
+ * moments and the SSIM map in double precision, mean over positions and channels.
+ * a, b: device fp32 [T, C, H, W]; data_range = L of c1 = (0.01 L)^2, c2 = (0.03 L)^2: 1 for [0,1] floats,
+ * 255 for [0,255] values (the reference's uint8 images); ssim: device fp32 [T].  Enqueued on `stream`. */
+int bsvd_ssim(const float* a, const float* b, int T, int C, int H, int W, int crop_border, float data_range,
+              float* ssim, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, then waits for
  * completion.  This is the end-to-end entry the bench's `e2e` number goes through. */
 int bsvd_forward_clip_host(bsvd_handle* h, const float* in_host, const float* noise_map_host,
@@ -145,6 +154,9 @@ int bsvd_host_last_output(bsvd_handle* h, float** dev_out);
 int bsvd_stream_push(bsvd_handle* h, const float* frame, const float* noise_map, float* out,
                      int in_c, int H, int W, int* produced, void* stream);
 int bsvd_reset(bsvd_handle* h);
+/* Steady-state pushes (from the 18th frame of a stream on) replay one CUDA graph per ring phase instead of
+ * issuing 32 launches; this counts the replays so far (BSVD_B200_NO_STREAM_GRAPH=1 disables them). */
+long long bsvd_stream_graph_replays(const bsvd_handle* h);
 
 /* -- multi-GPU plumbing: one-sided exchange over NVLink through peer-mapped memory ---------
  * replaces the reference's DataParallel scatter/gather (BasicSR/basicsr/models/base_model.py:74-75) for

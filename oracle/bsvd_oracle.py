@@ -365,3 +365,33 @@ def psnr_float(img, ref, crop_border: int = 2) -> float:
     b = ref[..., crop_border:-crop_border, crop_border:-crop_border].double()
     mse = float(((a - b) ** 2).mean())
     return float("inf") if mse == 0 else float(-10.0 * np.log10(mse))
+
+
+def ssim(img, ref, crop_border: int = 0, data_range: float = 1.0) -> float:
+    """calculate_ssim / _ssim (BasicSR/basicsr/metrics/psnr_ssim.py:49-128) on CHW arrays, restated without
+    cv2: 11x11 Gaussian window (cv2.getGaussianKernel(11, 1.5) = normalised exp(-(i-5)^2 / (2*1.5^2))),
+    'valid' correlation (the [5:-5, 5:-5] slice of cv2.filter2D), float64, mean over positions, then over
+    channels.  The reference works on [0,255] images (data_range 255); [0,1] floats with data_range 1 give
+    the same value."""
+    import numpy as np
+    a = np.asarray(img, dtype=np.float64)
+    b = np.asarray(ref, dtype=np.float64)
+    if crop_border:
+        a = a[:, crop_border:-crop_border, crop_border:-crop_border]
+        b = b[:, crop_border:-crop_border, crop_border:-crop_border]
+    k = np.exp(-((np.arange(11) - 5.0) ** 2) / (2 * 1.5 * 1.5))
+    k /= k.sum()
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+
+    def filt(x):          # separable 'valid' correlation with outer(k, k)
+        h = sum(k[i] * x[:, i:x.shape[1] - 10 + i] for i in range(11))
+        return sum(k[i] * h[i:h.shape[0] - 10 + i, :] for i in range(11))
+
+    vals = []
+    for ch in range(a.shape[0]):
+        x, y = a[ch], b[ch]
+        mu1, mu2 = filt(x), filt(y)
+        s11, s22, s12 = filt(x * x) - mu1 * mu1, filt(y * y) - mu2 * mu2, filt(x * y) - mu1 * mu2
+        m = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s11 + s22 + c2))
+        vals.append(m.mean())
+    return float(np.mean(vals))

@@ -31,6 +31,12 @@ CASES = [
     ("64to128_ps_skip_epilogue", 2, 6, 72, 64, 128, P | K),       # skip added in the epilogue (N tile 128)
     ("128to256_ps_only", 2, 6, 72, 128, 256, P),
     ("tiny_4x4", 2, 4, 4, 64, 64, R),
+    # stride 2 through the sub-plane boxes (conv_tc.cuh PIPE 4): ragged widths / heights, one-tile images
+    ("64to128_s2_plain", 2, 10, 260, 64, 128, R | D),
+    ("64to128_s2_shift_wide", 2, 6, 516, 64, 128, R | D | S),
+    ("64to128_s2_shift_tiny", 3, 4, 4, 64, 128, R | D | S),
+    ("128to256_s2_shift_odd_rows", 2, 14, 100, 128, 256, R | D | S),
+    ("128to256_s2_plain_tiny", 1, 2, 2, 128, 256, R | D),
 ]
 
 

@@ -484,7 +484,7 @@ def test_fp16_range_guard_flags_overflow_and_bf16_does_not():
     # blow up the un-activated PixelShuffle conv of temp1's upc1 (its output is stored without ReLU6)
     key = [k for k in sd if "nets_list.0.upc1.convblock.1.weight" in k][0]
     sd_big = dict(sd)
-    sd_big[key] = sd[key] * 3.0e4
+    sd_big[key] = sd[key] * 1.0e6        # weights ~2e4 (finite in fp16), outputs ~1e6
     from bsvd_b200.arch import BSVD
     for prec, want in (("fp16", True), ("bf16", False)):
         net = BSVD(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64,
@@ -577,3 +577,24 @@ def test_stream_100_frames_bf16_full_size_bit_identical_to_clip_prefix():
         ys = torch.cat(outs)
         yc = net(torch.cat(seq)[None])[0]
     assert torch.equal(ys, yc)
+
+
+def test_ssim_on_device_matches_calculate_ssim():
+    """bsvd_ssim against the oracle restatement of calculate_ssim (psnr_ssim.py:49-128, pinned against the
+    reference in tests/test_oracle.py): float [0,1] frames and [0,255] values, crop_border 0 and 2, sizes
+    that do not divide the 16x16 tiles."""
+    from bsvd_b200 import pipeline
+    for (T, H, W, cb) in ((3, 47, 61, 0), (2, 64, 80, 2), (1, 11, 11, 0), (2, 540, 960, 2)):
+        x, clean = O.make_synthetic_clip(T, H, W, seed=40 + H)
+        a, b = x[:, :3].clamp(0, 1).contiguous(), clean.contiguous()
+        got = pipeline.ssim_per_frame(a.cuda(), b.cuda(), crop_border=cb).cpu()
+        for t in range(T):
+            want = O.ssim(a[t].numpy(), b[t].numpy(), crop_border=cb)
+            assert abs(float(got[t]) - want) < 2e-6, (H, W, cb, t, float(got[t]), want)
+        a8, b8 = (a * 255).round(), (b * 255).round()
+        got8 = pipeline.ssim_per_frame(a8.cuda(), b8.cuda(), crop_border=cb, data_range=255.0).cpu()
+        want8 = O.ssim(a8[0].numpy(), b8[0].numpy(), crop_border=cb, data_range=255.0)
+        assert abs(float(got8[0]) - want8) < 2e-6
+    from bsvd_b200 import capi
+    with pytest.raises(capi.BsvdError):
+        pipeline.ssim_per_frame(torch.zeros(1, 3, 10, 20).cuda(), torch.zeros(1, 3, 10, 20).cuda())

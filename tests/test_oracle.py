@@ -114,3 +114,33 @@ def test_temporal_shift_edges():
     assert torch.equal(s[:, 4:], x[:, 4:])
     one = O.temporal_shift(x[:1])
     assert float(one[:, :4].abs().sum()) == 0.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference") and not os.path.isdir(
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "BasicSR")),
+    reason="needs the reference checkout (build container) or its staged copy")
+def test_ssim_restatement_matches_reference_calculate_ssim():
+    """Pin oracle.ssim against the reference's own calculate_ssim (cv2.filter2D formulation) on uint8-like
+    images, with and without crop_border, and check the [0,1]/data_range=1 equivalence."""
+    import numpy as np
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_root = "/root/reference" if os.path.isdir("/root/reference") else os.path.join(root, "baseline", "_ref")
+    sys.path.append(os.path.join(ref_root, "BasicSR"))
+    import types
+    if "basicsr.version" not in sys.modules:
+        ver = types.ModuleType("basicsr.version")
+        ver.__version__, ver.__gitsha__, ver.version_info = "1.3.4.2", "unknown", (1, 3, 4, 2)
+        sys.modules["basicsr.version"] = ver
+    from basicsr.metrics.psnr_ssim import calculate_ssim
+    rng = np.random.RandomState(0)
+    clean = rng.rand(40, 52, 3)
+    clean = (clean + np.roll(clean, 1, 0) + np.roll(clean, 1, 1)) / 3
+    a = np.clip(clean * 255, 0, 255).round()
+    b = np.clip((clean + 0.05 * rng.randn(40, 52, 3)) * 255, 0, 255).round()
+    for cb in (0, 2):
+        want = calculate_ssim(a, b, crop_border=cb, input_order="HWC")
+        got = O.ssim(a.transpose(2, 0, 1), b.transpose(2, 0, 1), crop_border=cb, data_range=255.0)
+        assert abs(want - got) < 1e-9, (cb, want, got)
+        got01 = O.ssim(a.transpose(2, 0, 1) / 255.0, b.transpose(2, 0, 1) / 255.0, crop_border=cb, data_range=1.0)
+        assert abs(want - got01) < 1e-9

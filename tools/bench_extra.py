@@ -191,6 +191,10 @@ def torch_gpu(args):
 
 
 def tiles(args):
+    """BASELINE.json configs[4]: one 4K clip cut into rows x cols spatial tiles, one per GPU.
+    --exchange p2p  (default) neighbour-only strips and output centres through peer-mapped memory with
+                    copy engines over NVLink (bsvd_b200.tiling.TileExchange), steps overlapped;
+    --exchange nccl the round-1 variant: all_gather of whole input tiles and of the outputs."""
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -204,43 +208,93 @@ def tiles(args):
     plan = tiling.tile_plan(H, W, args.rows, args.cols)
     t = plan[rank]
     # every rank synthesises the same frame and keeps only its own tile (stands for a decoder that
-    # delivers tiles); the 80-px ring then comes from the neighbours through the all_gather
+    # delivers tiles); the 80-px ring then comes from the neighbours
     x, _ = O.make_synthetic_clip(T, H, W, seed=1)
     x_tile = x[:, :, t.y0:t.y1, t.x0:t.x1].contiguous().to(dev)
     fwd = lambda r: net(r[None])[0]  # noqa: E731
+    ex, consumer, chk = None, None, None
+    if args.exchange == "p2p":
+        ex = tiling.TileExchange(T, 4, H, W, args.rows, args.cols, owner=0)
+        consumer = torch.cuda.Stream(device=dev)
+        chk = torch.zeros((), dtype=torch.float64, device=dev)
+    ev = torch.cuda.Event()
+    counter = [0]
+    last_full = [None]
 
     def step():
         with torch.no_grad():
-            return tiling.forward_tiled_distributed(fwd, x_tile, H, W, args.rows, args.cols)
+            if ex is None:
+                last_full[0] = tiling.forward_tiled_distributed(fwd, x_tile, H, W, args.rows, args.cols)
+                return
+            i = counter[0]
+            counter[0] += 1
+            full = ex.step(fwd, x_tile, i)
+            if rank == 0:
+                with torch.cuda.stream(consumer):
+                    ex.wait_full(i)
+                    chk.add_(full[:, 0, ::270, ::480].double().sum())     # touch the assembled frame
+                    last_full[0] = full
+                    ex.release_full(i)
 
-    for _ in range(2):
-        full = step()
+    def drain():
+        if consumer is not None:
+            ev.record(consumer)
+            torch.cuda.current_stream(dev).wait_event(ev)
+        if ex is not None:
+            ev.record(ex.pg.side)
+            torch.cuda.current_stream(dev).wait_event(ev)
+
+    for _ in range(3):
+        step()
+    drain()
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        full = step()
+        step()
+    drain()
     e1.record()
     dist.barrier()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    exact = None
+    exact, single_ms = None, None
     if args.check and rank == 0:
         with torch.no_grad():
-            whole = net(x[None].to(dev))[0]
-        exact = bool(torch.equal(whole, full))
+            xd = x[None].to(dev)
+            whole = net(xd)[0]
+            exact = bool(torch.equal(whole, last_full[0]))
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(2):
+                net(xd)
+            s1.record()
+            torch.cuda.synchronize()
+            single_ms = s0.elapsed_time(s1) / 2
     if rank == 0:
-        print(json.dumps({
-            "metric": f"denoised frames/sec at {H}x{W} (c=64)", "value": T / (float(ms) / 1e3),
+        fps = T / (float(ms) / 1e3)
+        line = {
+            "metric": f"denoised frames/sec at {H}x{W} (c=64)", "value": fps,
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "ms_per_step": float(ms),
             "scaling": "strong", "dtype": args.precision,
             "config": {"workload": f"BSVD-64 {H}x{W} {T}-frame clip, {args.rows}x{args.cols} spatial "
-                                   f"tiles, one per GPU, {tiling.HALO}-px input ring exchanged by NCCL "
-                                   "all_gather over NVLink, outputs all_gathered "
-                                   "(BASELINE.json configs[4], bit-exact variant)"},
-            "bit_exact_vs_single_gpu": exact}), flush=True)
+                                   f"tiles, one per GPU, {tiling.HALO}-px input ring (BASELINE.json configs[4], bit-exact variant)",
+                       "exchange": ("neighbour-only strips + output centres: copy-engine puts into peer-mapped buffers over "
+                                    "NVLink, double-buffered and overlapped across steps" if ex is not None
+                                    else "NCCL all_gather of whole input tiles and of the outputs")},
+            "bit_exact_vs_single_gpu": exact}
+        if ex is not None:
+            line["received_bytes_per_step"] = ex.received_bytes
+            line["ring_bytes"] = ex.ring_bytes
+            line["redundant_compute"] = sum((q.hy1 - q.hy0) * (q.hx1 - q.hx0) for q in plan) / float(H * W)
+        if single_ms is not None:
+            line["single_gpu"] = {"ms_per_clip": single_ms, "value": T / (single_ms / 1e3)}
+            line["strong_scaling_efficiency"] = fps / (T / (single_ms / 1e3)) / world
+        print(json.dumps(line), flush=True)
+    if ex is not None:
+        ex.close()
     dist.destroy_process_group()
 
 
@@ -255,6 +309,7 @@ if __name__ == "__main__":
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     a = ap.parse_args()
     if a.mode == "torch":
         a.frames = a.frames or 10
