@@ -109,7 +109,7 @@ static int make_map_pix(CUtensorMap* m, const void* base, int T, long long t_str
   return 0;
 }
 
-// Raw network input for the first conv's TMA loader: fp32 planes [planes][H][W]; box = [box_planes][4][132].
+// Raw network input for the first conv's TMA loader: fp32 planes [planes][H][W]; box = [box_planes][4][136].
 static int make_map_raw(CUtensorMap* m, const void* base, long long planes, int H, int W, int box_planes) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");

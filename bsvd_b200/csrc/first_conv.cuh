@@ -10,7 +10,7 @@
 //   warp  8    MMA issuer (8 MMAs per 2-row tile, filter bank resident)
 //   warps 9-16 epilogue (shared with conv_tc.cuh: bias, ReLU6, staged coalesced NHWC stores)
 //   warp  17   RAW instances only: TMA loader of the raw fp32 tiles
-// RAW = true (plain fp32 NCHW input, no reflection): the haloed raw tile [4 planes][4 rows][132 px] of
+// RAW = true (plain fp32 NCHW input, no reflection): the haloed raw tile [4 planes][4 rows][136 px] of
 // every tile is fetched by TMA into a 6-deep shared-memory ring, several tiles ahead (out-of-bounds = the
 // conv's zero padding), and the producers read their 48 values with conflict-free LDS.  With direct global
 // loads (RAW = false: uint8 / reflect-padded callers) each producer thread sits on 48 scalar LDGs of DRAM
@@ -30,10 +30,16 @@ constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
 constexpr size_t kFirstSmem = 1024 + kFirstStages * kFirstAStage + kFirstW + 8 * 2 * kStageBytesPerWarp;
 // raw-tile ring of the RAW instances
 constexpr int kRawStages = 6;
-constexpr int kRawPx = 132;                                  // 130 needed; 132 * 4 B is a multiple of 16 B
+constexpr int kRawPx = 136;                                  // columns x0-4 .. x0+131: a TMA box must START on a 16-byte
+                                                             // boundary of the innermost dimension (x0-1 on fp32 raises
+                                                             // 'illegal instruction', tools/probes/tma_probe.cu), and 136
+                                                             // makes a plane (4 rows) a multiple of 128 B, the alignment a
+                                                             // TMA destination needs (the noise-map plane is its own box)
+constexpr int kRawLead = 4;                                  // columns in front of x0 (3 unused + the halo column)
 constexpr int kRawRows = kFirstR + 2;
-constexpr uint32_t kRawPlane = kRawRows * kRawPx * 4;        // 2112 B
-constexpr uint32_t kRawStage = 4 * kRawPlane;                // 8448 B (4 channel planes)
+constexpr uint32_t kRawPlane = kRawRows * kRawPx * 4;        // 2176 B
+constexpr uint32_t kRawStage = 4 * kRawPlane;                // 8704 B (4 channel planes)
+static_assert(kRawPlane % 128 == 0, "TMA destinations must be 128-byte aligned");
 constexpr size_t kFirstSmemRaw = kFirstSmem + kRawStages * kRawStage;
 constexpr int kFirstThreadsRaw = kFirstThreads + 32;
 
@@ -156,10 +162,10 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
                            : (nmap && c == in_c ? nmap + static_cast<long long>(tc.t) * plane : nullptr);
       const float fill = p.use_sigma ? p.sigma_const : 0.f;      // constant noise map (inside the image)
       if constexpr (RAW) {
-        // the loader warp's TMA box [4 planes][4 rows][132 px] starts at (x0 - 1, y0 - 1): zero outside
+        // the loader warp's TMA box [4 planes][4 rows][136 px] starts at (x0 - 4, y0 - 1): zero outside
         const uint32_t rs = it % kRawStages, rp = (it / kRawStages) & 1;
         mbar_wait(raw_full(rs), rp);
-        const uint32_t src = raw_base + rs * kRawStage + i * 4;
+        const uint32_t src = raw_base + rs * kRawStage + (i + kRawLead - 1) * 4;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -248,8 +254,8 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         mbar_wait(raw_empty(rs), rp ^ 1);
         mbar_expect_tx(raw_full(rs), tx);
         const uint32_t dst = raw_base + rs * kRawStage;
-        tma_load_3d(dst, &map_raw, raw_full(rs), tc.x0 - 1, tc.y0 - 1, tc.t * in_c);
-        if (nm_planes) tma_load_3d(dst + in_c * kRawPlane, &map_rawnm, raw_full(rs), tc.x0 - 1, tc.y0 - 1, tc.t);
+        tma_load_3d(dst, &map_raw, raw_full(rs), tc.x0 - kRawLead, tc.y0 - 1, tc.t * in_c);
+        if (nm_planes) tma_load_3d(dst + in_c * kRawPlane, &map_rawnm, raw_full(rs), tc.x0 - kRawLead, tc.y0 - 1, tc.t);
       }
     }
   } else if (warp == 8) {

@@ -69,6 +69,48 @@ def stub_optional_dependencies():
         dali.plugin = plug
 
 
+def ensure_legacy_nvidia_smi():
+    """profile.py:5-6 picks its GPU with `nvidia-smi -q -d Memory | grep -A4 GPU | grep Free`, which relies on
+    the pre-R515 layout (Total / Used / Free directly under the GPU line).  Current drivers print a `Reserved`
+    line as well, the pipe matches nothing and the script dies in np.argmax before importing torch.  When that
+    is the case, put a pass-through `nvidia-smi` wrapper in front of PATH that answers exactly this query in the
+    old layout (real numbers from --query-gpu) and forwards everything else to the real binary."""
+    import os
+    import shutil
+    import stat
+    import subprocess
+    import tempfile
+    real = shutil.which("nvidia-smi")
+    if real is None:
+        return None
+    try:
+        out = subprocess.run("nvidia-smi -q -d Memory | grep -A4 GPU | grep Free", shell=True, capture_output=True,
+                             text=True, timeout=60).stdout
+        if any(len(l.split()) >= 3 and l.split()[2].isdigit() for l in out.splitlines()):
+            return None                      # the script's own parse works here
+    except Exception:  # noqa: BLE001
+        pass
+    d = tempfile.mkdtemp(prefix="bsvd_b200_smi_")
+    w = os.path.join(d, "nvidia-smi")
+    with open(w, "w") as f:
+        f.write(f"""#!/bin/sh
+if [ "$1" = "-q" ] && [ "$2" = "-d" ] && [ "$3" = "Memory" ]; then
+  {real} --query-gpu=pci.bus_id,memory.total,memory.used,memory.free --format=csv,noheader,nounits | \\
+  while IFS=, read bus total used free; do
+    echo "GPU $bus"; echo "    FB Memory Usage"
+    echo "        Total                             :$total MiB"
+    echo "        Used                              :$used MiB"
+    echo "        Free                              :$free MiB"
+  done
+else
+  exec {real} "$@"
+fi
+""")
+    os.chmod(w, os.stat(w).st_mode | stat.S_IXUSR | stat.S_IXGRP | stat.S_IXOTH)
+    os.environ["PATH"] = d + os.pathsep + os.environ.get("PATH", "")
+    return w
+
+
 def run_reference_script(path: str, reference_root: str):
     """`python -m bsvd_b200.plugin <reference_root> profile.py`: run an unmodified reference entry
     point (profile.py, run_test.py) with the B200 class installed under ARCH_REGISTRY['BSVD']."""
@@ -80,6 +122,7 @@ def run_reference_script(path: str, reference_root: str):
     import json
     reference_root = os.path.abspath(reference_root)
     stub_optional_dependencies()
+    ensure_legacy_nvidia_smi()
     install()
     from .arch import BSVD
     atexit.register(lambda: print("bsvd_b200.plugin: " + json.dumps(BSVD.stats), flush=True))

@@ -54,7 +54,7 @@ def test_profile_py_runs_unchanged_through_the_plugin(tmp_path):
     stats = json.loads(m.group(1))
     assert stats["instances"] >= 1 and stats["forward_calls"] >= 10, stats
     assert stats["kernel_launches"] == 32 * stats["forward_calls"], stats
-    assert "B200-native BSVD-64" in out                           # print(model) shows our module
+    assert "test function name: <class 'bsvd_b200.arch.BSVD'>" in out   # profile.py:41 names what it times
     assert "output shape is torch.Size([1, 10, 3, 540, 960])" in out
     t = re.findall(r"loops, mean of best \d+: ([0-9.]+) sec per loop", out)
     assert t, out[-2000:]
