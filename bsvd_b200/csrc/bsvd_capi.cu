@@ -188,6 +188,15 @@ struct StageSpec {
   bool relu6 = false, relu = false, pixshuf = false, skip = false, shift = false;
   bool resid_in = false, final_out = false, first_im2col = false;
   bool stacked = false;   // 64->64 stride-1 stage with the vertical taps stacked in N (conv_tc.cuh mode 2)
+  // c32 configurations, native layout: a 32-channel full-resolution tensor [H][W][32] is the same memory as
+  // [H][W/2][64], so a 3x3 conv over 32 channels runs as a 3x3 conv over pixel PAIRS with 64 "channels"
+  // (column n = a*32 + co of pixel 2x+a, K index b*32 + ci of pixel 2x'+b, weight W[dy][2 dxp + b - a] or 0):
+  // half of that GEMM multiplies structural zeros, but these stages are HBM-bound and now move 32 channels
+  // per pixel instead of 64 zero-padded ones.
+  bool pairx = false;       // stride-1 pair conv (physical 64 -> 64 on an image of W/2 pairs)
+  bool pair_s2 = false;     // stride-2 conv reading pairs (conv_tc.cuh PIPE 5): 6 (dy, pair) taps
+  bool pair_final = false;  // last conv (32 -> 3) on pairs (final_conv.cuh PAIR instances)
+  int store_c = 0;          // first conv: channels actually stored when fewer than the GEMM's 64 columns
   // derived
   int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
   void derive() {
@@ -206,10 +215,12 @@ struct StageSpec {
     stacked = stack_on && cta2_on && cin == 64 && cout == 64 && stride == 1 && !first_im2col &&
               !final_out && !pixshuf && !skip;
     if (stacked) { tap_begin = 0; tap_end = 3; }   // three dx slabs of [192 rows per CTA][64]
+    if (pair_s2) { tap_begin = 0; tap_end = 6; }
   }
   int ntaps() const { return tap_end - tap_begin; }
   int n_tiles() const { return gemm_n / ntile; }
   size_t pack_elems() const {
+    if (pair_final) return (size_t)3 * kFinalNPair * kChunk;   // [pair tap][dy*8+a*4+co][64]
     if (final_out) return (size_t)3 * kFinalN * kChunk;   // [dx][dy*3+co][64]
     if (stacked) return (size_t)3 * 2 * 192 * kChunk;     // [dx][cta rank][192 rows][64]
     return (size_t)n_tiles() * cin_chunks * ntaps() * ntile * kChunk;
@@ -229,11 +240,74 @@ static inline int col_to_cout(const StageSpec& s, int col) {
 // its eight 16-byte chunks XOR-swizzled by (row & 7) (SWIZZLE_128B K-major canonical layout).
 static void pack_weights(const StageSpec& s, const float* w, const float* b, int bf16,
                          std::vector<uint16_t>& pack, std::vector<float>& bias) {
+  if (s.pairx) {
+    // expand to the dense 64 -> 64 pair conv and pack that like any other 64 -> 64 stage
+    std::vector<float> wp((size_t)64 * 64 * 9, 0.f), bp(64, 0.f);
+    for (int a = 0; a < 2; ++a)
+      for (int co = 0; co < s.cout_l; ++co) {
+        bp[a * 32 + co] = b ? b[co] : 0.f;
+        for (int bb = 0; bb < 2; ++bb)
+          for (int ci = 0; ci < s.cin_l; ++ci)
+            for (int dy = 0; dy < 3; ++dy)
+              for (int dxp = -1; dxp <= 1; ++dxp) {
+                const int dx = 2 * dxp + bb - a;
+                if (dx < -1 || dx > 1) continue;
+                wp[((size_t)(a * 32 + co) * 64 + (bb * 32 + ci)) * 9 + dy * 3 + (dxp + 1)] =
+                    w[((size_t)co * s.cin_l + ci) * 9 + dy * 3 + (dx + 1)];
+              }
+      }
+    StageSpec d = s;
+    d.pairx = false; d.cin_l = 64; d.cout_l = 64;
+    pack_weights(d, wp.data(), bp.data(), bf16, pack, bias);
+    return;
+  }
   pack.assign(s.pack_elems(), 0);
   bias.assign(s.gemm_n, 0.f);
   for (int col = 0; col < s.gemm_n; ++col) {
     const int co = col_to_cout(s, col);
     if (co >= 0 && co < s.cout_l) bias[col] = b ? b[co] : 0.f;
+  }
+  if (s.pair_final) {
+    // final_conv.cuh PAIR layout: slab = pair tap dxp, row n = dy*8 + a*4 + co, K = b*32 + ci
+    for (int dxp = -1; dxp <= 1; ++dxp)
+      for (int dy = 0; dy < 3; ++dy)
+        for (int a = 0; a < 2; ++a)
+          for (int co = 0; co < s.cout_l; ++co) {
+            const int n = dy * 8 + a * 4 + co;
+            for (int bb = 0; bb < 2; ++bb) {
+              const int dx = 2 * dxp + bb - a;
+              if (dx < -1 || dx > 1) continue;
+              for (int ci = 0; ci < s.cin_l && ci < 32; ++ci) {
+                const int k = bb * 32 + ci;
+                const float v = w[((size_t)co * s.cin_l + ci) * 9 + dy * 3 + (dx + 1)];
+                pack[((size_t)(dxp + 1) * kFinalNPair + n) * kChunk + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = to16(v, bf16);
+              }
+            }
+          }
+    return;
+  }
+  if (s.pair_s2) {
+    // conv_tc.cuh PIPE 5: six slabs in consumption order (dy0,x-1) (dy0,x) (dy2,x-1) (dy2,x) (dy1,x-1) (dy1,x);
+    // output pixel x reads input columns 2x-1 (pair x-1, b=1), 2x (pair x, b=0), 2x+1 (pair x, b=1)
+    static const int kDy[6] = {0, 0, 2, 2, 1, 1};
+    for (int j = 0; j < 6; ++j) {
+      const int dy = kDy[j], dxp = (j & 1) ? 0 : -1;
+      uint16_t* blk = pack.data() + (size_t)j * s.ntile * kChunk;
+      for (int n = 0; n < s.ntile; ++n) {
+        const int co = col_to_cout(s, n);
+        if (co < 0 || co >= s.cout_l) continue;
+        for (int bb = 0; bb < 2; ++bb) {
+          const int dx = (dxp == -1) ? (bb == 1 ? 0 : -1) : 1 + bb;    // tap column index 0..2, -1 = none
+          if (dx < 0) continue;
+          for (int ci = 0; ci < s.cin_l && ci < 32; ++ci) {
+            const int k = bb * 32 + ci;
+            const float v = w[((size_t)co * s.cin_l + ci) * 9 + dy * 3 + dx];
+            blk[(size_t)n * kChunk + (((k >> 3) ^ (n & 7)) << 3) + (k & 7)] = to16(v, bf16);
+          }
+        }
+      }
+    }
+    return;
   }
   if (s.final_out) {
     // final_conv.cuh layout: slab dx, row n = dy*3 + co, 64 input channels, SW128-swizzled rows
@@ -395,6 +469,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
   p.T = io.T; p.H = Ho; p.W = Wo;
   p.overflow = io.overflow;
+  p.pair_px = s.pairx ? 1 : 0;
   p.cin_chunks = s.cin_chunks;
   p.n_tiles = s.n_tiles();
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
@@ -408,11 +483,12 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.total_tiles = p.positions;
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = (s.relu ? EPI_RELU : EPI_RELU6) | (bf16 ? EPI_BF16 : 0);
-    p.out = io.out; p.out_C = s.cout; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = 6;
-    p.out_frame_stride = (long long)Ho * Wo * s.cout;
+    const int oc = s.store_c ? s.store_c : s.cout;     // 32: only the first unit of every row is stored
+    p.out = io.out; p.out_C = oc; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = (oc == 32) ? 5 : 6;
+    p.out_frame_stride = (long long)Ho * Wo * oc;
     L->cta2 = 0;
     if (make_map_pix(&L->map_o, io.out, io.out_T ? io.out_T : io.T,
-                     io.out_T ? io.out_T_stride : p.out_frame_stride * 2, Ho, Wo, s.cout, 0, 32, 32,
+                     io.out_T ? io.out_T_stride : p.out_frame_stride * 2, Ho, Wo, oc, 0, 32, 32,
                      CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     p.tma_out = 1; p.stg_bytes_per_warp = 2 * kStageBytesPerWarp;
     L->map = L->map_o; L->map_w = L->map_o; L->map_s = L->map_o;
@@ -436,8 +512,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     if (make_map_halo(&L->map, io.in, io.T, io.H, io.W, s.cin, s.rows)) return 1;
     L->map_w = L->map;
     L->grid = std::min(p.total_tiles, num_sms());
-    L->smem = kFinalSmem;
-    L->ntile = 16; L->rows = s.rows;
+    L->smem = s.pair_final ? kFinalSmemPair : kFinalSmem;
+    L->ntile = s.pair_final ? 17 : 16; L->rows = s.rows;     // 16 / 17: final_conv_kernel, per pixel / per pair
     return 0;
   }
   p.positions = p.T * p.yblocks * p.xblocks;
@@ -453,7 +529,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if (stacked) p.mode = 2;
   // stride 2: sub-plane boxes (conv_tc.cuh PIPE 4) unless BSVD_B200_S2_TAPS=1 asks for the per-tap boxes
   static const int s2_taps = [] { const char* e = getenv("BSVD_B200_S2_TAPS"); return (e && e[0] == '1') ? 1 : 0; }();
-  const bool s2_boxes = p.mode == 1 && cta2 && !s2_taps && !desc_variant;
+  const bool s2_boxes = p.mode == 1 && cta2 && ((!s2_taps && !desc_variant) || s.pair_s2);
+  if (s.pair_s2 && !cta2) return fail("the pair stride-2 stage needs the CTA-pair kernel");
   if (p.mode != 1) {
     p.a_tx_bytes = (uint32_t)(s.rows + 2) * kRowBytes;
     p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
@@ -470,7 +547,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     }
   } else if (s2_boxes) {
     // one box per input sub-plane: ring slots sized for the largest, (R+1) rows x 129 px
-    p.mode = 4;
+    p.mode = s.pair_s2 ? 5 : 4;
     p.a_tx_bytes = (uint32_t)(s.rows + 1) * kS2BoxPx * 128u;
     p.a_stage_bytes = (uint32_t)align_up(p.a_tx_bytes, 1024);
     p.a_stages = 3;
@@ -519,9 +596,10 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
 
-  const int cin_map = s.first_im2col ? kChunk : s.cin;
+  // pair stride-2: the [T][H/2][2][W/2][2*32] view of the 32-channel tensor has the pairs as its pixels
+  const int cin_map = s.first_im2col ? kChunk : (s.pair_s2 ? 32 : s.cin);
   int rc = (s.stride != 2) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
-           : (p.mode == 4) ? make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows + 1, kS2BoxPx)
+           : (p.mode >= 4) ? make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows + 1, kS2BoxPx)
                            : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
   if (rc) return rc;
   if (cta2) {
@@ -531,7 +609,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     L->map_w = L->map;   // unused
   }
   L->map_s = L->map; L->map_o = L->map;   // unused unless set below
-  if (p.mode == 4) {   // even input rows: R-row boxes (the skip map slot is free: stride-2 stages have no skip)
+  if (p.mode >= 4) {   // even input rows: R-row boxes (the skip map slot is free: stride-2 stages have no skip)
     rc = make_map_s2(&L->map_s, io.in, io.T, io.H, io.W, cin_map, s.rows, kS2BoxPx);
     if (rc) return rc;
   }
@@ -592,13 +670,15 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
 
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
   if (L.ntile == -1) return launch_first(L, st);
-  if (L.ntile == 16) {
+  if (L.ntile == 16 || L.ntile == 17) {
     static std::atomic<bool> attr_done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
-      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmem));
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmemPair));
+      CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinalSmemPair));
       attr_done[dev & 63] = true;
     }
     cudaLaunchConfig_t cfg;
@@ -609,8 +689,14 @@ static int launch_stage(const StageLaunch& L, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (L.p.flags & EPI_BF16) CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<true>, L.map, L.p));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<false>, L.map, L.p));
+    const bool bf = (L.p.flags & EPI_BF16) != 0;
+    if (L.ntile == 17) {
+      if (bf) CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<true, true>, L.map, L.p));
+      else CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<false, true>, L.map, L.p));
+    } else {
+      if (bf) CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<true, false>, L.map, L.p));
+      else CUDA_TRY(cudaLaunchKernelEx(&cfg, final_conv_kernel<false, false>, L.map, L.p));
+    }
     return 0;
   }
   if (L.ntile == 64 && L.rows == 2) return launch_one<64, 2>(L, st);
@@ -665,6 +751,7 @@ static const int kBlockDelay = 8;   // latency of one DenBlock in steps (8 BiBuf
 struct bsvd_handle {
   bsvd_config cfg;
   int bf16 = 0;
+  int pair32 = 0;               // c32 configurations in their native layout (32 channels at full resolution)
   int cp[3] = {64, 128, 256};   // channels of the full / half / quarter resolution tensors as stored
   StageDev stages[BSVD_NUM_LAYERS];
   // ---- clip-mode workspace / plan (rebuilt when T,H,W change) ----
@@ -794,9 +881,21 @@ static void build_specs(bsvd_handle* h) {
     set(15, c0, out_ch, false);
     S(15).resid_in = (blk == 0); S(15).final_out = (blk == 1);
     if (blk == 1) S(15).cout = out_ch;                                // 3 output planes, no padding
+    if (h->pair32) {
+      // native layout of the c32 configurations (see StageSpec::pairx): full-resolution tensors hold 32
+      // channels per pixel and are processed as pixel pairs; nothing below full resolution is padded
+      S(0).cout = 64; S(0).store_c = 32;                       // first conv: 64-column GEMM, 32 channels stored
+      if (blk == 1) { S(0).pairx = true; S(0).store_c = 0; }
+      S(1).pairx = true;
+      S(2).pair_s2 = true;                                     // cin 64 = one pair, cout = c1
+      S(13).cout = 4 * (c0);                                   // PixelShuffle to 32 channels: no padding
+      S(14).pairx = true;
+      if (blk == 0) S(15).pairx = true; else S(15).pair_final = true;
+    }
     for (int l = 0; l < 16; ++l) S(l).derive();
   }
-  h->cp[0] = pad64(h->cfg.chns[0]); h->cp[1] = pad64(h->cfg.chns[1]); h->cp[2] = pad64(h->cfg.chns[2]);
+  h->cp[0] = h->pair32 ? 32 : pad64(h->cfg.chns[0]);
+  h->cp[1] = pad64(h->cfg.chns[1]); h->cp[2] = pad64(h->cfg.chns[2]);
 }
 
 extern "C" { static void free_stream(bsvd_handle* h); }
@@ -842,7 +941,9 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     auto plan = [&](int l, const void* src, int sh, int sw, void* dst, const void* skip = nullptr,
                     int skip_C = 0, long long skip_fs = 0) -> int {
       StageIO io;
-      io.in = src; io.T = T; io.H = sh; io.W = sw; io.out = dst;
+      const StageSpec& sp = h->stages[blk * 16 + l].spec;
+      // pair stages see an image of W/2 pixel pairs (same memory)
+      io.in = src; io.T = T; io.H = sh; io.W = (sp.pairx || sp.pair_final) ? sw / 2 : sw; io.out = dst;
       io.skip = skip; io.skip_C = skip_C; io.skip_frame_stride = skip_fs;
       io.overflow = h->d_overflow;
       if (blk == 0 && l == 15) { io.resid_in = in; io.resid_C = in_c; io.aux_out = h->bufS; }
@@ -919,6 +1020,11 @@ int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
   h->cfg = *cfg;
   h->device = dev;
   h->bf16 = (cfg->precision == BSVD_PREC_BF16);
+  {
+    // BSVD_B200_C32_PADDED=1: the round-1 path (every channel count below 64 zero-padded to 64)
+    const char* e = getenv("BSVD_B200_C32_PADDED");
+    h->pair32 = (c32 && !(e && e[0] == '1') && use_cta2_default()) ? 1 : 0;
+  }
   build_specs(h);
   if (cudaMalloc((void**)&h->d_overflow, sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(h->d_overflow, 0, sizeof(unsigned)) != cudaSuccess) {
@@ -1358,6 +1464,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       const size_t in_bytes = ring_slot_bytes(h, in_ring, H, W);
       StageIO io;
       io.T = 1; io.H = H / r; io.W = W / r;
+      if (sd.spec.pairx || sd.spec.pair_final) io.W /= 2;      // pixel pairs (same memory)
       io.overflow = h->d_overflow;
       io.in = S.ring[in_blk][in_ring];
       io.out = S.ring[b][kLayerOut[l]];          // patched per step
@@ -1377,13 +1484,13 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
       const int nslots = kRingSlots[in_ring];
       SL.maps.resize(nslots);
-      const int cin_map = sd.spec.first_im2col ? kChunk : sd.spec.cin;
+      const int cin_map = sd.spec.first_im2col ? kChunk : (sd.spec.pair_s2 ? 32 : sd.spec.cin);
       if (b == 0 && l == 0 && raw_tma_ok(S.raw, nullptr, W)) {
         SL.raw_maps.resize(9);
         for (int k = 0; k < 9; ++k)
           if (make_map_raw(&SL.raw_maps[k], S.raw + (size_t)k * 4 * H * W, h->cfg.in_ch, H, W, h->cfg.in_ch)) return 1;
       }
-      const bool s2b = SL.tmpl.p.mode == 4;
+      const bool s2b = SL.tmpl.p.mode >= 4;
       if (s2b) SL.maps2.resize(nslots);
       for (int k = 0; k < nslots; ++k) {
         const void* base = S.ring[in_blk][in_ring] + (size_t)k * in_bytes;

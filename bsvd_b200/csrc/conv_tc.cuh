@@ -57,12 +57,34 @@ constexpr int kMaxBias = 512;
 //   box 0 (py1,px1): taps 0,2,6,8   box 1 (py1,px0): taps 1,7   box 2 (py0,px1): taps 3,5   box 3 (py0,px0): tap 4
 // A tap's operand is its box offset by (row, col) 128-byte pixels, exactly like the halo tile.
 constexpr int kS2BoxPx = kRunPx + 1;                       // 129 pixels per box row
-__host__ __device__ constexpr int s2_tap(int j) {           // j-th tap in consumption order
+// PIPE 5 is the same pipeline for a 32-channel input read as pixel PAIRS ([H][W/2][64], see the c32
+// configurations in bsvd_capi.cu): the stride-2 conv then strides only in y, output pixel x reads pairs x-1
+// and x, so there are two boxes (odd rows: R+1 rows, even rows: R rows, both starting at pair x0-1) and six
+// (dy, pair) taps whose filter slabs the host packs in consumption order:
+//   box 0 (py1): (dy0,x-1) (dy0,x) (dy2,x-1) (dy2,x)     box 1 (py0): (dy1,x-1) (dy1,x)
+template <int PIPE> __host__ __device__ constexpr int s2_ntaps() { return PIPE == 5 ? 6 : 9; }
+template <int PIPE> __host__ __device__ constexpr int s2_slab(int j) {     // filter slab of the j-th tap consumed
+  if (PIPE == 5) return j;
   return j == 0 ? 0 : j == 1 ? 2 : j == 2 ? 6 : j == 3 ? 8 : j == 4 ? 1 : j == 5 ? 7 : j == 6 ? 3 : j == 7 ? 5 : 4;
 }
-__host__ __device__ constexpr int s2_box(int j) { return j < 4 ? 0 : j < 6 ? 1 : j < 8 ? 2 : 3; }
-__host__ __device__ constexpr bool s2_box_first(int j) { return j == 0 || s2_box(j) != s2_box(j - 1); }
-__host__ __device__ constexpr bool s2_box_last(int j) { return j == 8 || s2_box(j) != s2_box(j + 1); }
+template <int PIPE> __host__ __device__ constexpr int s2_box(int j) {
+  if (PIPE == 5) return j < 4 ? 0 : 1;
+  return j < 4 ? 0 : j < 6 ? 1 : j < 8 ? 2 : 3;
+}
+template <int PIPE> __host__ __device__ constexpr bool s2_box_first(int j) { return j == 0 || s2_box<PIPE>(j) != s2_box<PIPE>(j - 1); }
+template <int PIPE> __host__ __device__ constexpr bool s2_box_last(int j) {
+  return j == s2_ntaps<PIPE>() - 1 || s2_box<PIPE>(j) != s2_box<PIPE>(j + 1);
+}
+template <int PIPE> __host__ __device__ constexpr int s2_box_py(int b) { return PIPE == 5 ? (b == 0) : (b < 2); }
+template <int PIPE> __host__ __device__ constexpr int s2_box_px(int b) { return PIPE == 5 ? 0 : (b == 0 || b == 2); }
+template <int PIPE> __host__ __device__ constexpr int s2_row_off(int j) {   // box row of output row 0's operand
+  if (PIPE == 5) return (j == 2 || j == 3) ? 1 : 0;
+  return (s2_slab<4>(j) / 3 == 2) ? 1 : 0;
+}
+template <int PIPE> __host__ __device__ constexpr int s2_col_off(int j) {   // box column of output pixel 0's operand
+  if (PIPE == 5) return j & 1;
+  return (s2_slab<4>(j) % 3 == 2) ? 1 : 0;
+}
 
 // masks of epilogue features a kernel instance is compiled with
 enum : int {
@@ -89,7 +111,7 @@ struct ConvParams {
   int positions;        // T*yblocks*xblocks pixel tiles
   int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2, generic pipeline only),
                         // 2 = halo with the vertical taps stacked in N (64->64 stages, see below),
-                        // 4 = stride 2 with one box per input sub-plane (see s2_tap)
+                        // 4 = stride 2 with one box per input sub-plane (see s2_slab)
   int w_rows_cta;       // CTA pair: filter rows one CTA stages per W stage
   int cin_total;        // Cin (stride-2 coordinate math)
   // ---- pipeline ----
@@ -144,6 +166,10 @@ struct ConvParams {
   // PixelShuffle + skip convs, temp1's output, every stage of an act='relu' model) set this sticky flag
   // when a value they store is inf/NaN, so an overflow can never pass silently (bsvd_overflow_flag)
   unsigned* overflow;
+  // c32 configurations: a 32-channel full-resolution tensor is processed as pixel PAIRS ([H][W/2][64]); the
+  // stage's W then counts pairs and GEMM column n = a*32 + co is channel co of pixel 2*x + a.  Only the
+  // residual / compact-copy code of temp1's last conv needs to know (EPI_RESID_IN).
+  int pair_px;
 };
 // reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
 __device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }
@@ -481,7 +507,7 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
-  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0;
+  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0, pair_px;
   uint32_t stg_bytes_per_warp;
   int src_H, src_W;
   void* out; void* out_prev; void* out_next; void* aux_out;
@@ -492,8 +518,8 @@ struct EpiParams {
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
-        out_t0(p.out_t0), stg_bytes_per_warp(p.stg_bytes_per_warp),
-        src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : p.W),
+        out_t0(p.out_t0), pair_px(p.pair_px), stg_bytes_per_warp(p.stg_bytes_per_warp),
+        src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W)),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), overflow(p.overflow), out_frame_stride(p.out_frame_stride),
         skip_frame_stride(p.skip_frame_stride) {}
@@ -615,16 +641,19 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
         }
       }
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
-        if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid) {
+        // pair mode: unit 0 / 1 of a row hold pixel 2x / 2x+1, each with its own channels 0..2
+        const bool resid_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
+        if ((flags & EPI_RESID_IN) && j == 0 && resid_unit && valid) {
           // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
           if (use_rin) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) f[i] = rin[i] - f[i];
           } else {
-            const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : p.W;
+            const int xr = p.pair_px ? 2 * x + (nbase >> 5) : x;
+            const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W);
             const long long plane = static_cast<long long>(sH) * sW;
             const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
-                             static_cast<long long>(reflect_src(y, sH)) * sW + reflect_src(x, sW);
+                             static_cast<long long>(reflect_src(y, sH)) * sW + reflect_src(xr, sW);
 #pragma unroll
             for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
           }
@@ -633,8 +662,11 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
       o[j].z = pack2<BF16>(f[4], f[5]); o[j].w = pack2<BF16>(f[6], f[7]);
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
-        if ((flags & EPI_RESID_IN) && j == 0 && nbase == 0 && valid && p.aux_out) {
-          const long long pix = (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
+        const bool aux_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
+        if ((flags & EPI_RESID_IN) && j == 0 && aux_unit && valid && p.aux_out) {
+          const long long pix = p.pair_px
+              ? (static_cast<long long>(tc.t) * p.H + y) * (2 * p.W) + 2 * x + (nbase >> 5)
+              : (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
           reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o[j].x, o[j].y);
         }
       }
@@ -771,6 +803,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 //   0 halo tile + streamed filter slabs   1 stride-2 per-tap boxes + streamed slabs (generic only)
 //   2 stacked 64->64 (resident bank)      3 generic: mode / w_resident read from ConvParams
 //   4 stride-2 sub-plane boxes + streamed slabs (map_s = the R-row box map of the even input rows)
+//   5 the same on a 32-channel input read as pixel pairs (stride 2 in y only; c32 configurations)
 template <int NTILE, int R, bool BF16, bool CTA2, int MASK, int EW, int PIPE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -881,7 +914,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0;
     uint32_t a_stage_bytes, w_stage_bytes, a_tx_bytes;
   } const pp = {p.a_stages, p.w_stages, p.cin_chunks, PIPE == 3 ? p.tap_begin : 0,
-                PIPE == 3 ? p.tap_end : (PIPE == 2 ? 3 : 9),
+                PIPE == 3 ? p.tap_end : (PIPE == 2 ? 3 : PIPE == 5 ? 6 : 9),
                 PIPE == 3 ? p.mode : PIPE, PIPE == 3 ? p.w_resident : (PIPE == 2 ? 1 : 0),
                 p.total_tiles, p.desc_variant, p.skip_mma, p.w_rows_cta, p.cin_total, p.out_C_log2, p.out_C,
                 p.skip_t0, p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
@@ -898,25 +931,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = tile0; tile < pp.total_tiles; tile += tstep) {
         const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
         int nskip = 0;
-        if constexpr (PIPE == 4 && CTA2) {
-          // stride 2, sub-plane boxes: 4 A boxes + 9 filter slabs per chunk, issued in consumption order
+        if constexpr ((PIPE == 4 || PIPE == 5) && CTA2) {
+          // stride 2, sub-plane boxes: the A boxes and filter slabs of a chunk, issued in consumption order
           for (int c = 0; c < pp.cin_chunks; ++c) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-              if (s2_box_first(j)) {
-                const int b = s2_box(j);
-                const int py = (b < 2) ? 1 : 0, px = (b == 0 || b == 2) ? 1 : 0;
+            for (int j = 0; j < s2_ntaps<PIPE>(); ++j) {
+              if (s2_box_first<PIPE>(j)) {
+                const int b = s2_box<PIPE>(j);
+                const int py = s2_box_py<PIPE>(b), px = s2_box_px<PIPE>(b);
                 const uint32_t bytes = static_cast<uint32_t>((py ? R + 1 : R) * kS2BoxPx * 128);
                 mbar_wait(a_empty(sa), pa ^ 1);
                 if (rank == 0) mbar_expect_tx(a_full(sa), 2 * bytes);
                 tma_load_5d_2sm(a_base + sa * pp.a_stage_bytes, py ? &map_a : &map_s, a_full(sa),
-                                px * pp.cin_total + c * kChunk, px ? tc.x0 - 1 : tc.x0, py,
+                                px * pp.cin_total + c * kChunk, (px || PIPE == 5) ? tc.x0 - 1 : tc.x0, py,
                                 py ? tc.y0 - 1 : tc.y0, tc.t);
                 if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
               }
               mbar_wait(w_empty(sw), pw ^ 1);
               if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
-              const size_t blk = static_cast<size_t>(tc.nt * pp.cin_chunks + c) * 9 + s2_tap(j);
+              const size_t blk = static_cast<size_t>(tc.nt * pp.cin_chunks + c) * s2_ntaps<PIPE>() + s2_slab<PIPE>(j);
               tma_load_2d_2sm(w_base + sw * pp.w_stage_bytes, &map_w, w_full(sw), 0,
                               (static_cast<int>(blk) * 2 + static_cast<int>(rank)) * pp.w_rows_cta);
               if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
@@ -1068,20 +1101,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + buf * kAccCols;
         int nskip = 0;
-        if constexpr (PIPE == 4 && CTA2) {
+        if constexpr ((PIPE == 4 || PIPE == 5) && CTA2) {
           for (int c = 0; c < pp.cin_chunks; ++c) {
             uint32_t a_lo0 = 0;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-              if (s2_box_first(j)) {
+            for (int j = 0; j < s2_ntaps<PIPE>(); ++j) {
+              if (s2_box_first<PIPE>(j)) {
                 mbar_wait(a_full(sa), pa);
                 a_lo0 = a_lo_base + sa * a_lo_step;
               }
               mbar_wait(w_full(sw), pw);
               tc_fence_after();
-              const int tap = s2_tap(j);
-              const int dy = tap / 3, dx = tap % 3;
-              const int ro = (dy == 2) ? 1 : 0, co = (dx == 2) ? 1 : 0;     // offset inside the sub-plane box
+              const int ro = s2_row_off<PIPE>(j), co = s2_col_off<PIPE>(j);   // offset inside the sub-plane box
               const uint32_t b_lo0 = w_lo_base + sw * w_lo_step;
               const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
               if (leader) {
@@ -1094,11 +1125,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                  idesc, (k > 0) ? 1u : first);
                 }
                 umma_commit_2sm(w_empty(sw));
-                if (s2_box_last(j)) umma_commit_2sm(a_empty(sa));
+                if (s2_box_last<PIPE>(j)) umma_commit_2sm(a_empty(sa));
               }
               __syncwarp();
               if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
-              if (s2_box_last(j)) {
+              if (s2_box_last<PIPE>(j)) {
                 if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
               }
             }
@@ -1220,8 +1251,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int y = tn.y0 + u0 / G, x = tn.x0 + quad * 32 + lane;
           if (tn.nt * NTILE + (u0 % G) * 32 == 0 && tn.t < e.T && y < e.H && x < e.W) {
             const long long plane = static_cast<long long>(e.src_H) * e.src_W;
+            const int xr = e.pair_px ? 2 * x : x;          // unit 0 of a pair row is pixel 2x
             const float* r = e.resid_in + (static_cast<long long>(tn.t) * e.resid_C) * plane +
-                             static_cast<long long>(reflect_src(y, e.src_H)) * e.src_W + reflect_src(x, e.src_W);
+                             static_cast<long long>(reflect_src(y, e.src_H)) * e.src_W + reflect_src(xr, e.src_W);
 #pragma unroll
             for (int i = 0; i < 3; ++i) rin_next[i] = __ldg(r + i * plane);
           }

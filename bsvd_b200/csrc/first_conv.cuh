@@ -260,7 +260,8 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     }
   } else if (warp == 8) {
     // ====================================== MMA issuer ======================================
-    const uint32_t idesc = make_idesc(NT, BF16 ? 1 : 0);
+    // 32 output channels (c32 configurations): N = 32, the accumulator keeps its 64-column row pitch
+    const uint32_t idesc = make_idesc(p.out_C == 32 ? 32 : NT, BF16 ? 1 : 0);
     const uint32_t leader = elect_one();
     constexpr uint32_t kDescHi = 0x40000000u | (1u << 14) | (1024u >> 4);
     const uint64_t desc_hi = static_cast<uint64_t>(kDescHi) << 32;
@@ -309,17 +310,33 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
-      const int u0 = half * 2;                 // 4 units (2 rows x 2 column groups), 2 per warp half
-      uint32_t va[32], vb[32];
+      constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
       const uint4 nosk[4] = {};
       const float norin[3] = {};
+      if (p.out_C == 32) {
+        // 32 output channels: one unit per image row, one row per warp half; the two staging tiles alternate
+        // per tile (one bulk group per tile: the group awaited before a tile is rewritten is two tiles old)
+        uint32_t va[32];
+        tmem_ld32(tacc + half * NT, va);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
+        float bv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[i];
+        epilogue_unit<BF16, kEpiMask>(p, tc, el, tc.y0 + half, 0, va, nosk, bv, stg + (it & 1u) * kStageBytesPerWarp, quad, lane,
+                                      norin, false, &map_o);
+        continue;
+      }
+      const int u0 = half * 2;                 // 4 units (2 rows x 2 column groups), 2 per warp half
+      uint32_t va[32], vb[32];
       tmem_ld32(tacc + (u0 / G) * NT + (u0 % G) * 32, va);
       tmem_ld32(tacc + ((u0 + 1) / G) * NT + ((u0 + 1) % G) * 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
-      constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
       float bv[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[(u0 % G) * 32 + i];

@@ -56,6 +56,12 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
         return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 4>(L, st);
       return fail("no stride-2 kernel instance for this stage (NTILE=%d R=%d)", NTILE, R);
     }
+    if (mode == 5) {
+      // the same on pixel pairs (c32 configurations: 32 -> 64 channels, full -> half resolution)
+      if constexpr (NTILE == 64 && R == 2 && (MASK & (EPI_PIXSHUF | EPI_RESID_IN | EPI_TMA_OUT)) == 0)
+        return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 5>(L, st);
+      return fail("no pair stride-2 kernel instance for this stage (NTILE=%d R=%d)", NTILE, R);
+    }
     if (L.p.desc_variant != 0 || L.p.tap_begin != 0 || L.p.tap_end != (mode == 2 ? 3 : 9)) {
       // debug switches / partial tap ranges only exist in the generic pipeline
     } else if constexpr (NTILE == 64 && R == 2) {
@@ -107,6 +113,7 @@ constexpr int kMaskResid = kMaskAct | EPI_RESID_IN;
 constexpr int kMaskUpTma = EPI_PIXSHUF | EPI_TMA_OUT;   // upc1.convblock.0: units leave through TMA stores
 constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0 with the skip on the tensor core (opt-in)
 constexpr int kMaskUpSkipShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0: skip added in the epilogue
+constexpr int kMaskUpSkip = EPI_PIXSHUF | EPI_SKIP;                    // c32 upc1.convblock.0 (N tile 128)
 constexpr int kMaskAll = kMaskAct | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
@@ -122,6 +129,10 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
     if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain, 8>(L, st);
     if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskShift, 8>(L, st);
     if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid, 8>(L, st);
+    if constexpr (NTILE == 128 && R == 2) {
+      // c32 upc1.convblock.0 (64 -> 128, PixelShuffle to 32 channels + skip added in the epilogue)
+      if ((f & ~kMaskUpSkip) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpSkip, 8>(L, st);
+    }
     if constexpr (NTILE == 256 && R == 1) {
       if (L.p.tma_out && (f & ~kMaskUpTma) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpTma, 8>(L, st);
       if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, BF16, true, kMaskUpShift, 8>(L, st);
