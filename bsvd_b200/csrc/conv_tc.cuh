@@ -627,6 +627,11 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       }
     }
     uint4 o[4];
+    // range guard: running maximum of what this lane stores (|x|, or x under ReLU, which clamps the
+    // negative side); ReLU6 stages are bounded and skip it
+    const bool chk_range = !BF16 && !(flags & EPI_RELU6) && p.overflow != nullptr;
+    const bool chk_signed = (flags & EPI_RELU) != 0;
+    float vmax = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float f[8];
@@ -659,6 +664,19 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
           }
         }
       }
+      if constexpr (!BF16) {
+        if (chk_range) {
+          if (chk_signed) {
+            vmax = fmaxf(fmaxf(vmax, f[0]), fmaxf(f[1], f[2]));
+            vmax = fmaxf(fmaxf(vmax, f[3]), fmaxf(f[4], f[5]));
+            vmax = fmaxf(vmax, fmaxf(f[6], f[7]));
+          } else {
+            vmax = fmaxf(fmaxf(vmax, fabsf(f[0])), fmaxf(fabsf(f[1]), fabsf(f[2])));
+            vmax = fmaxf(fmaxf(vmax, fabsf(f[3])), fmaxf(fabsf(f[4]), fabsf(f[5])));
+            vmax = fmaxf(vmax, fmaxf(fabsf(f[6]), fabsf(f[7])));
+          }
+        }
+      }
       o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
       o[j].z = pack2<BF16>(f[4], f[5]); o[j].w = pack2<BF16>(f[6], f[7]);
       if constexpr ((MASK & EPI_RESID_IN) != 0) {
@@ -679,16 +697,9 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       }
     }
     if constexpr (!BF16) {
-      // fp16 range guard (see ConvParams::overflow): exponent field all ones in either half
-      if (!(flags & EPI_RELU6) && p.overflow) {
-        uint32_t bad = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          bad |= ((o[j].x & 0x7fff7fffu) + 0x04000400u) | ((o[j].y & 0x7fff7fffu) + 0x04000400u) |
-                 ((o[j].z & 0x7fff7fffu) + 0x04000400u) | ((o[j].w & 0x7fff7fffu) + 0x04000400u);
-        }
-        if (__any_sync(0xffffffffu, valid && (bad & 0x80008000u)) && lane == 0) atomicOr(p.overflow, 1u);
-      }
+      // fp16 range guard (see ConvParams::overflow): a value that rounds to inf (|x| >= 65520).  A NaN can
+      // only come from an inf stored by an earlier stage, which raised the (sticky) flag there.
+      if (chk_range && __any_sync(0xffffffffu, valid && !(vmax < 65520.f)) && lane == 0) atomicOr(p.overflow, 1u);
     }
     if constexpr ((MASK & EPI_TMA_OUT) != 0) {
       // the TMA store that last read this staging tile (the previous unit's, or with two tiles per

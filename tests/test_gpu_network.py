@@ -598,3 +598,37 @@ def test_ssim_on_device_matches_calculate_ssim():
     from bsvd_b200 import capi
     with pytest.raises(capi.BsvdError):
         pipeline.ssim_per_frame(torch.zeros(1, 3, 10, 20).cuda(), torch.zeros(1, 3, 10, 20).cuda())
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: c32 configurations in their native layout (pixel-pair stages, bsvd_capi.cu StageSpec::pairx)
+# ---------------------------------------------------------------------------------------------------
+def test_c32_native_full_size_stream_graphs_and_odd_crop():
+    """(a) 540x960 against the oracle; (b) a 30-frame stream (graph replays from the 18th push on, ring slots
+    of the pair stages) bit-identical to the clip schedule; (c) the fused pad/clamp/crop entry on an odd
+    size (the pair final conv crops a half-used last pair) against its unfused steps."""
+    from bsvd_b200 import pipeline
+    net, layers = _make_c32(7, 0.5)
+    x, _ = O.make_synthetic_clip(3, 540, 960, seed=71)
+    x3 = x[:, :3].contiguous()
+    with torch.no_grad():
+        y = net(x3[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x3, act=O.C32["act"])
+    assert float((y - ref).abs().max()) <= TOL["fp16"]
+    assert not net.overflowed()
+    xs, _ = O.make_synthetic_clip(30, 36, 132, seed=72)
+    xs3 = xs[:, :3].contiguous()
+    with torch.no_grad():
+        yc = net(xs3[None].cuda())[0]
+        net.reset()
+        outs, _ = _drive_stream(net, xs3)
+        net.reset()
+    assert torch.equal(torch.cat([o for o in outs if o is not None]), yc)
+    assert net.stream_graph_replays() >= 12
+    xo, _ = O.make_synthetic_clip(2, 31, 45, seed=73)
+    noisy = xo[:, :3].clamp(0, 1).contiguous().cuda()
+    with torch.no_grad():
+        a = net.denoise_sequence(noisy, None)
+        xp, (ph, pw) = pipeline.pad_to_multiple_of_4(noisy)
+        b = net(xp[None])[0].clamp(0, 1)[..., :31, :45]
+    assert torch.equal(a, b)
