@@ -541,6 +541,14 @@ def run_b200(args):
                   "scaled by ms_per_step / (sum of stage times) so that they add up to the timed step",
         "hbm": {"achieved": dom["bytes"] / (dom_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": dom["bytes"] / (dom_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        # the two power regimes side by side (see timing_note): `achieved` / `frac` belong to `value`'s timed
+        # region (a burst after a pause) and are set against the SUSTAINED cuBLAS peak as in round 1;
+        # the like-for-like pairs are burst vs burst and sustained vs sustained
+        "frac_vs_burst_peak": ach_tf / peaks["tflops_burst"],
+        "sustained_regime": {
+            "achieved": dom["flops"] / (dom["ms"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": dom["flops"] / (dom["ms"] * 1e-3) / 1e12 / peak_tf,
+            "note": "per-launch times of the profiled pass, which runs back to back behind the sustained block"},
     }
     ms_1gpu = ms_step if world == 1 else ms_step_profiled
     whole = {

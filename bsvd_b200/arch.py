@@ -163,7 +163,7 @@ class BSVD(nn.Module):
             if p not in ("fp16", "bf16"):
                 raise ValueError("precision must be 'fp16' or 'bf16'")
             return p
-        w = self.temp1.inc.convblock._modules['0'].weight
+        w = self._first_weight()
         if w.dtype == torch.bfloat16:
             return "bf16"
         if torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16:
@@ -172,8 +172,11 @@ class BSVD(nn.Module):
         # fp32 accumulation: 11-bit significands, the same operand precision as TF32.
         return "fp16"
 
+    def _first_weight(self):
+        return self.temp1.inc.convblock._modules['0'].weight
+
     def _out_dtype(self):
-        w = self.temp1.inc.convblock._modules['0'].weight
+        w = self._first_weight()
         if torch.is_autocast_enabled():
             return torch.get_autocast_dtype('cuda')
         return w.dtype if w.dtype in (torch.float16, torch.bfloat16) else torch.float32
@@ -211,7 +214,7 @@ class BSVD(nn.Module):
 
     def _module_device(self):
         """Device of the parameters when they are on a GPU, else the current CUDA device."""
-        w = self.temp1.inc.convblock._modules['0'].weight
+        w = self._first_weight()
         return w.device if w.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
     def _destroy(self):
@@ -234,8 +237,9 @@ class BSVD(nn.Module):
         return super()._apply(fn, *a, **k)
 
     # ---------------------------------------------------------------- clip mode
-    def _run_stream(self, x, noise_map=None):
-        """x: [T,C,H,W] on a CUDA device -> [T,3,H,W] (one continuous stream)."""
+    def _run_stream(self, x, noise_map=None, clip_len=None):
+        """x: [T,C,H,W] on a CUDA device -> [T,3,H,W]: one continuous stream, or (clip_len given) T/clip_len
+        independent clips of clip_len frames each in one pass (bsvd_forward_clips)."""
         if not x.is_cuda:
             x = x.cuda()          # the reference does x.cuda() per frame (bsvd_arch.py:520)
         dev = x.device
@@ -247,9 +251,16 @@ class BSVD(nn.Module):
                 nm = noise_map.detach().to(dev).float().contiguous()
             T, Cc, H, W = xf.shape
             out = torch.empty((T, 3, H, W), dtype=torch.float32, device=dev)
-            capi.check(lib.bsvd_forward_clip(
-                self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
-                out.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+            if clip_len is None or clip_len == T:
+                capi.check(lib.bsvd_forward_clip(
+                    self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
+                    out.data_ptr(), T, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
+            else:
+                if T % clip_len:
+                    raise ValueError(f"{T} frames cannot be split into clips of {clip_len}")
+                capi.check(lib.bsvd_forward_clips(
+                    self._handle, xf.data_ptr(), nm.data_ptr() if nm is not None else None,
+                    out.data_ptr(), T // clip_len, clip_len, Cc, H, W, torch.cuda.current_stream(dev).cuda_stream))
             BSVD.stats["forward_calls"] += 1
             BSVD.stats["kernel_launches"] += lib.bsvd_last_launch_count(self._handle)
         od = self._out_dtype()
@@ -259,12 +270,10 @@ class BSVD(nn.Module):
         """[N,F,C,H,W] (+ optional noise_map [N,F,1,H,W]) -> [N,F,3,H,W]  (bsvd_arch.py:490-499).
         Like the reference, N>1 clips form ONE continuous stream unless `independent_clips`."""
         N, Fr, Cc, H, W = input.shape
-        if self.independent_clips and N > 1:
-            outs = [self._run_stream(input[n], None if noise_map is None else noise_map[n])
-                    for n in range(N)]
-            return torch.stack(outs, dim=0)
         nm = None if noise_map is None else noise_map.reshape(N * Fr, 1, H, W)
-        out = self._run_stream(input.reshape(N * Fr, Cc, H, W), nm)
+        # independent clips: all N clips in ONE pass of the 32 stages, folds confined to each clip
+        out = self._run_stream(input.reshape(N * Fr, Cc, H, W), nm,
+                               clip_len=Fr if (self.independent_clips and N > 1) else None)
         return out.reshape(N, Fr, 3, H, W)
 
     def streaming_forward(self, input_seq):
@@ -429,6 +438,70 @@ class BSVD(nn.Module):
     def last_launch_count(self):
         return 0 if self._handle is None else capi.load_library().bsvd_last_launch_count(
             self._handle)
+
+
+class TSN(BSVD):
+    """Drop-in for the reference's training twin `TSN` (Experimental_root/archs/tsm_arch.py:10-72:
+    WNet_multistage + TemporalShift, shift_type 'TSM', shift_div 8) — FORWARD only, on the same kernels.
+
+    * parameters carry the TSN names (`base_model.nets_list.{0,1}.<block>...`), so the reference's TSN
+      checkpoints load with `load_state_dict` / `{'params': ...}` files as they are;
+    * eval mode = `batch_shift` (temporal_shift.py:53-80) over the whole [N*F] batch: one continuous stream
+      (the state a fresh `global_queue_buffer._init(0)` gives: no past buffer is consumed);
+    * train mode = `shift(x, n_segment)` (temporal_shift.py:27-49): the batch is `N*F / num_segments`
+      independent clips of `num_segments` frames, zero folds at every clip boundary (bsvd_forward_clips).
+
+    There is no backward pass: calling it with autograd enabled on parameters that require gradients
+    raises instead of silently returning a constant w.r.t. the weights."""
+
+    def __init__(self, num_segments=11, base_model='WNet_multistage', shift_type='TSM', shift_div=8,
+                 inplace=False, net2d_opt=None, enable_past_buffer=True, precision=None, **kwargs):
+        if base_model != 'WNet_multistage' or shift_type != 'TSM' or shift_div != 8 or inplace:
+            raise NotImplementedError("bsvd_b200.TSN implements base_model='WNet_multistage', shift_type='TSM', "
+                                      "shift_div=8, inplace=False (options/train/*.yml); no CPU/PyTorch fallback")
+        opt = dict(net2d_opt or {})
+        opt.pop("pretrain_ckpt", None)
+        super().__init__(pretrain_ckpt=None, precision=precision, **opt)
+        self.num_segments = int(num_segments)
+        # re-home the 32 convs under the TSN names (same Conv2d objects, same execution order)
+        convs = self._convs()
+        del self.temp1, self.temp2
+        self.base_model = _Node()
+        self.base_model.add_module("nets_list", _Node())
+        names = []
+        for blk in range(2):
+            root = _Node()
+            self.base_model.nets_list.add_module(str(blk), root)
+            for i, (_stem, tsn) in enumerate(_LAYERS):
+                _attach(root, tsn, convs[blk * 16 + i])
+                names.append(f"base_model.nets_list.{blk}.{tsn}")
+        self._param_names = names
+
+    def _first_weight(self):
+        return self.base_model.nets_list._modules['0'].inc.convblock._modules['0'].weight
+
+    def load_tsn_state(self, ckpt_state):
+        first = list(ckpt_state.keys())[0]
+        sd = {(k[len('module.'):] if first.startswith('module.') else k): v for k, v in ckpt_state.items()}
+        self.load_state_dict(sd, strict=True)
+        self._weights_sig = None
+
+    def forward(self, input, noise_map=None):
+        """[N,F,C,H,W] (or [N*F,C,H,W]) -> same leading shape with 3 channels (tsm_arch.py:59-72)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("bsvd_b200.TSN has no backward pass: run the training-mode forward under "
+                                      "torch.no_grad() (validation inside a training loop), train with the reference")
+        if noise_map is not None:
+            input = torch.cat([input, noise_map], dim=2 if input.dim() == 5 else 1)
+        five = input.dim() == 5
+        x = input.reshape(-1, *input.shape[-3:]) if five else input
+        clip = None
+        if self.training:
+            if x.shape[0] % self.num_segments:
+                raise RuntimeError(f"shape '[-1, {self.num_segments}, ...]' is invalid for {x.shape[0]} frames")
+            clip = self.num_segments
+        out = self._run_stream(x, None, clip_len=clip)
+        return out.reshape(*input.shape[:2], 3, *input.shape[-2:]) if five else out
 
 
 def params_to_numpy(module: BSVD):

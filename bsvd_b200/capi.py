@@ -22,7 +22,7 @@ EPI_RELU6, EPI_PIXSHUF, EPI_SKIP_ADD, EPI_SHIFT_STORE, EPI_STRIDE2 = 1, 2, 4, 8,
 # every symbol include/bsvd_b200.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "bsvd_create", "bsvd_destroy", "bsvd_last_error", "bsvd_version", "bsvd_set_weights",
-    "bsvd_layer_shape", "bsvd_forward_clip", "bsvd_forward_clip_host", "bsvd_stream_push",
+    "bsvd_layer_shape", "bsvd_forward_clip", "bsvd_forward_clips", "bsvd_forward_clip_host", "bsvd_stream_push",
     "bsvd_reset", "bsvd_last_launch_count", "bsvd_workspace_bytes", "bsvd_conv_stage",
     "bsvd_set_profiling", "bsvd_get_stage_ms", "bsvd_stage_info", "bsvd_last_stage_ms",
     "bsvd_forward_clip_host_async", "bsvd_host_sync", "bsvd_denoise_clip", "bsvd_psnr",
@@ -72,6 +72,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bsvd_set_weights.argtypes = [vp, ci, vp, vp, ci, ci]
     lib.bsvd_layer_shape.argtypes = [vp, ci, cip, cip, cip]
     lib.bsvd_forward_clip.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.bsvd_forward_clips.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.bsvd_forward_clip_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.bsvd_forward_clip_host_async.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.bsvd_host_sync.argtypes = [vp]

@@ -818,6 +818,7 @@ struct CallOpts {
   int use_sigma = 0, clamp01 = 0;
   float sigma_const = 0.f;
   int u8_io = 0, u8_bgr = 0;          // uint8 HWC frames in and out
+  int seg_T = 0;                      // > 0: the T frames are independent clips of seg_T frames each
 };
 
 // Every entry point runs on the device the handle was created on (weights, workspaces and tensor maps
@@ -1188,6 +1189,7 @@ static int forward_clip_impl(bsvd_handle* h, const float* in, const float* noise
     q.u8_bgr = o.u8_bgr; q.out_u8 = o.u8_io;
   }
   for (int l = 0; l < BSVD_NUM_LAYERS; ++l) {
+    h->plan[l].p.seg_T = o.seg_T;
     if (launch_stage(h->plan[l], st)) return 1;
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[l + 2], st));
     ++launches;
@@ -1202,6 +1204,17 @@ int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, f
   if (check_dev_ptr(h, in, "in") || check_dev_ptr(h, noise_map, "noise_map") || check_dev_ptr(h, out, "out"))
     return 1;
   return forward_clip_impl(h, in, noise_map, out, T, in_c, H, W, stream, CallOpts());
+}
+
+int bsvd_forward_clips(bsvd_handle* h, const float* in, const float* noise_map, float* out, int N, int T,
+                       int in_c, int H, int W, void* stream) {
+  if (!h || !in || !out) return fail("null argument");
+  if (N < 1 || T < 1) return fail("N and T must be >= 1 (got N=%d T=%d)", N, T);
+  if (check_dev_ptr(h, in, "in") || check_dev_ptr(h, noise_map, "noise_map") || check_dev_ptr(h, out, "out"))
+    return 1;
+  CallOpts o;
+  o.seg_T = T;
+  return forward_clip_impl(h, in, noise_map, out, N * T, in_c, H, W, stream, o);
 }
 
 static int denoise_clip_impl(bsvd_handle* h, const float* in, float sigma, float* out, int T, int H, int W,

@@ -170,6 +170,7 @@ struct ConvParams {
   // stage's W then counts pairs and GEMM column n = a*32 + co is channel co of pixel 2*x + a.  Only the
   // residual / compact-copy code of temp1's last conv needs to know (EPI_RESID_IN).
   int pair_px;
+  int seg_T;            // clip mode: frames per independent clip when the T frames are several clips (0 = one clip)
 };
 // reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
 __device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }
@@ -507,7 +508,7 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
-  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0, pair_px;
+  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0, pair_px, seg_T;
   uint32_t stg_bytes_per_warp;
   int src_H, src_W;
   void* out; void* out_prev; void* out_next; void* aux_out;
@@ -518,7 +519,7 @@ struct EpiParams {
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
-        out_t0(p.out_t0), pair_px(p.pair_px), stg_bytes_per_warp(p.stg_bytes_per_warp),
+        out_t0(p.out_t0), pair_px(p.pair_px), seg_T(p.seg_T), stg_bytes_per_warp(p.stg_bytes_per_warp),
         src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W)),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), overflow(p.overflow), out_frame_stride(p.out_frame_stride),
@@ -759,21 +760,25 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
       if ((flags & EPI_SHIFT) && up.cb < 2 * p.fold) {     // (uniform) only the unit holding the folds
         const int c0 = up.cb + 8 * j;
         uint16_t* own = dst;
+        // the T frames may be several independent clips of seg_T frames each (TSN train-mode shift,
+        // temporal_shift.py:27-49; bsvd_forward_clips): folds never cross a clip boundary
+        const int seg = p.seg_T > 0 ? p.seg_T : p.T;
+        const int ts = tc.t % seg;
         if (c0 < p.fold) {
           if (p.ring_mode) {
             dst = reinterpret_cast<uint16_t*>(p.out_prev);
             if (p.flags & EPI_ZERO_FUTURE) zdst = own;
           } else {
-            dst = (tc.t > 0) ? own - p.out_frame_stride : nullptr;
-            if (tc.t == p.T - 1) zdst = own;
+            dst = (ts > 0) ? own - p.out_frame_stride : nullptr;
+            if (ts == seg - 1) zdst = own;
           }
         } else if (c0 < 2 * p.fold) {
           if (p.ring_mode) {
             dst = reinterpret_cast<uint16_t*>(p.out_next);
             if (!p.out_prev) zdst = own;
           } else {
-            dst = (tc.t + 1 < p.T) ? own + p.out_frame_stride : nullptr;
-            if (tc.t == 0) zdst = own;
+            dst = (ts + 1 < seg) ? own + p.out_frame_stride : nullptr;
+            if (ts == 0) zdst = own;
           }
         }
       }

@@ -15,7 +15,7 @@ import sys
 import types
 
 
-def install(registry=None, import_reference_archs: bool = True):
+def install(registry=None, import_reference_archs: bool = True, install_tsn: bool = False):
     """Make ARCH_REGISTRY['BSVD'] resolve to the B200-native class.  Returns the previous entry."""
     from .arch import BSVD
     if registry is None:
@@ -30,6 +30,9 @@ def install(registry=None, import_reference_archs: bool = True):
         registry = importlib.import_module("basicsr.utils.registry").ARCH_REGISTRY
     prev = registry._obj_map.get("BSVD")
     registry._obj_map["BSVD"] = BSVD
+    if install_tsn:
+        from .arch import TSN
+        registry._obj_map["TSN"] = TSN      # forward-only twin (validation inside a training run)
     return prev
 
 

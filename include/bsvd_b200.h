@@ -90,6 +90,14 @@ int bsvd_layer_shape(const bsvd_handle* h, int layer, int* out_ch, int* in_ch, i
 int bsvd_forward_clip(bsvd_handle* h, const float* in, const float* noise_map, float* out,
                       int T, int in_c, int H, int W, void* stream);
 
+/* N independent clips of T frames each in ONE pass of the 32 stages (in / noise_map / out hold N*T frames,
+ * clip after clip): the temporal folds never cross a clip boundary.  This is the batch-of-clips
+ * configuration on one GPU and the arithmetic of the training twin's train-mode shift
+ * (TemporalShift.forward -> shift(x, n_segment), Experimental_root/archs/temporal_shift_ops/
+ * temporal_shift.py:27-49, with n_segment = T); bsvd_forward_clip is the N = 1 case. */
+int bsvd_forward_clips(bsvd_handle* h, const float* in, const float* noise_map, float* out, int N, int T,
+                       int in_c, int H, int W, void* stream);
+
 /* -- the callers either side of the path, fused -----------------------------------
  * replaces temp_denoise (Experimental_root/models/validation_seq_infer.py:10-31) together with
  * DenoisingModel.padding_input / crop_output (Experimental_root/models/denoising_model.py:133-168):

@@ -136,3 +136,37 @@ def test_header_is_valid_c_and_a_plain_c_client_links(tmp_path):
         assert "no CPU fallback" in out.stdout
     else:
         assert "layer 31: weight [3,64,3,3]" in out.stdout
+
+
+def test_frame_io_names_and_png_roundtrip(tmp_path):
+    """bsvd_b200.frames: the reference's file ordering rule (utils_common.py:78-95: by the integer made of all
+    digits of the path) and a lossless PNG write / read round trip."""
+    import numpy as np
+    from bsvd_b200 import frames
+    rng = np.random.RandomState(0)
+    seq = rng.randint(0, 256, size=(12, 20, 28, 3), dtype=np.uint8)
+    d = tmp_path / "seq"
+    paths = frames.write_sequence_u8(seq, str(d))
+    assert [os.path.basename(p) for p in paths][:3] == ["00000000.png", "00000001.png", "00000002.png"]
+    names = frames.get_imagenames(str(d))
+    assert [os.path.basename(n) for n in names] == [f"{i:08d}.png" for i in range(12)]
+    back = frames.read_sequence_u8(str(d))
+    assert back.dtype == np.uint8 and np.array_equal(back, seq)
+    assert frames.read_sequence_u8(str(d), max_num_fr=5).shape[0] == 5
+    with pytest.raises(FileNotFoundError):
+        frames.read_sequence_u8(str(tmp_path / "missing"))
+
+
+def test_tsn_twin_uses_the_reference_tsn_parameter_names():
+    """bsvd_b200.arch.TSN (forward-only twin of tsm_arch.TSN): its state_dict keys are the TSN checkpoint's."""
+    from bsvd_b200.arch import TSN
+    from oracle import bsvd_oracle as O
+    net = TSN(num_segments=4, net2d_opt=dict(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none',
+                                             interm_ch=64, act='relu6'))
+    sd = O.make_synthetic_params(0, 0.5)
+    assert sorted(net.state_dict().keys()) == sorted(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    net.load_tsn_state({"module." + k: v for k, v in sd.items()})
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 4, 4, 8, 8))            # no backward pass: refuses under autograd

@@ -632,3 +632,99 @@ def test_c32_native_full_size_stream_graphs_and_odd_crop():
         xp, (ph, pw) = pipeline.pad_to_multiple_of_4(noisy)
         b = net(xp[None])[0].clamp(0, 1)[..., :31, :45]
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: independent clips in one pass, the TSN twin (forward only), folder validation
+# ---------------------------------------------------------------------------------------------------
+def test_independent_clips_one_pass_equals_per_clip_calls_and_tsn_train_mode():
+    from bsvd_b200.arch import TSN
+    net, layers = make_net()
+    x, _ = O.make_synthetic_clip(12, 36, 72, seed=81)
+    xc = x.cuda()
+    with torch.no_grad():
+        net.independent_clips = True
+        batched = net(xc.reshape(3, 4, 4, 36, 72))                      # bsvd_forward_clips: N=3, T=4
+        net.independent_clips = False
+        singles = torch.stack([net(xc[None, 4 * i:4 * i + 4])[0] for i in range(3)])
+    assert torch.equal(batched, singles)
+    ref = torch.stack([O.forward_clip(layers, x[4 * i:4 * i + 4]) for i in range(3)])
+    assert float((batched.float().cpu() - ref).abs().max()) <= TOL["fp16"]
+    # the TSN twin: train mode = shift(x, n_segment) = independent clips of num_segments frames;
+    # eval mode = batch_shift over the whole batch = one stream
+    sd = O.make_synthetic_params(0, 0.5)
+    tsn = TSN(num_segments=4, net2d_opt=dict(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none',
+                                             interm_ch=64, act='relu6'))
+    tsn.load_state_dict(sd)
+    tsn = tsn.cuda()
+    with torch.no_grad():
+        tsn.train()
+        yt = tsn(xc.reshape(3, 4, 4, 36, 72))
+        tsn.eval()
+        ye = tsn(xc.reshape(3, 4, 4, 36, 72))
+        one = net(xc[None])[0]
+    assert torch.equal(yt, batched)
+    assert torch.equal(ye.reshape(12, 3, 36, 72), one)
+
+
+def test_tsn_twin_train_mode_matches_live_reference_tsn():
+    from baseline import reference_runner as R
+    if not R.available():
+        pytest.skip("baseline/_ref not staged")
+    from bsvd_b200.arch import TSN
+    REG, gqb = R.import_reference()
+    sd = O.make_synthetic_params(4, 0.5)
+    opt = dict(chns=[64, 128, 256], mid_ch=64, shift_input=False, norm='none', interm_ch=64, act='relu6')
+    ref = REG._obj_map["TSN"] if "TSN" in REG._obj_map else None
+    import importlib
+    ref_cls = importlib.import_module("Experimental_root.archs.tsm_arch").TSN
+    ref_net = ref_cls(num_segments=5, base_model='WNet_multistage', shift_type='TSM', shift_div=8, inplace=False,
+                      net2d_opt=dict(opt))
+    ref_net.load_state_dict(sd, strict=True)
+    ref_net = ref_net.cuda().train()
+    ours = TSN(num_segments=5, net2d_opt=dict(opt))
+    ours.load_state_dict(sd)
+    ours = ours.cuda().train()
+    x, _ = O.make_synthetic_clip(10, 40, 56, seed=82)
+    xc = x.cuda().reshape(2, 5, 4, 40, 56)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = ref_net(xc)
+            got = ours(xc)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= TOL["fp16"]
+
+
+def test_denoise_folder_reads_pngs_writes_pngs_and_reports_metrics(tmp_path):
+    from bsvd_b200 import frames, pipeline
+    net, _ = make_net()
+    _, clean = O.make_synthetic_clip(5, 46, 62, seed=83)               # odd size: pad / crop inside the kernels
+    src = frames.to_u8_bgr(clean).numpy()
+    frames.write_sequence_u8(src, str(tmp_path / "in"))
+    out = frames.denoise_folder(net, str(tmp_path / "in"), str(tmp_path / "out"), valnoisestd=20.0, seed=3,
+                                crop_border=2, suffix="_bsvd")
+    assert out["frames"] == 5 and len(out["paths"]) == 5 and os.path.basename(out["paths"][0]) == "00000000_bsvd.png"
+    # the same steps by hand
+    dev = torch.device("cuda")
+    fr = torch.from_numpy(src).to(dev)
+    gt = frames.to_float_rgb(fr)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    noisy = gt + torch.randn(gt.shape, generator=g, device=dev) * (20.0 / 255.0)
+    with torch.no_grad():
+        res = pipeline.denoise_sequence_unfused(net, noisy, 20.0 / 255.0)
+    assert np.array_equal(frames.read_sequence_u8(str(tmp_path / "out")), frames.to_u8_bgr(res).cpu().numpy())
+    for t in range(5):
+        assert abs(float(out["psnr"][t]) - O.psnr_float(res[t].cpu(), gt[t].cpu(), crop_border=2)) < 1e-3
+        want = O.ssim(frames.to_u8_bgr(res)[t].permute(2, 0, 1).float().cpu().numpy(),
+                      fr[t].permute(2, 0, 1).float().cpu().numpy(), crop_border=2, data_range=255.0)
+        assert abs(float(out["ssim"][t]) - want) < 2e-6
+    # already-noisy uint8 input: frame entry, no metrics
+    out2 = frames.denoise_folder(net, str(tmp_path / "in"), None, valnoisestd=20.0, add_noise=False)
+    with torch.no_grad():
+        direct = net.denoise_frames_u8(fr, 20.0 / 255.0, bgr=True)
+    assert out2["psnr"] is None and np.array_equal(out2["result_u8"], direct.cpu().numpy())
