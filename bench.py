@@ -583,6 +583,35 @@ def run_b200(args):
               "sample": f"[1,{n_par},4,{H},{W}] (the timed clip, all {n_par} frames) vs fp32 CPU oracle",
               "fp16_overflow_flag": overflow}
     parity["ok"] = bool(parity["max_abs"] <= tol and not overflow)
+
+    # ---- fp32-grade mode (precision='fp32x3': hi/lo fp16 pairs, three tensor-core products per contraction)
+    # on the same clip: for callers that run the reference with val.fp16 False and TF32 off
+    fp32_grade = None
+    if world == 1 and not args.no_fp32x3 and n_par == T_CLIP:
+        try:
+            net3 = make_net("fp32x3", dev, sd)
+            with torch.no_grad():
+                for _ in range(2):
+                    y3 = net3(x_dev[None])[0]
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(4):
+                    y3 = net3(x_dev[None])[0]
+                f1.record()
+                torch.cuda.synchronize()
+            ms3 = f0.elapsed_time(f1) / 4
+            d3 = (y3.float().cpu() - ref).abs()
+            fp32_grade = {"precision": "fp32x3", "value": T_CLIP / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+                          "max_abs": float(d3.max()), "mean_abs": float(d3.mean()), "tolerance": 1e-4,
+                          "sample": f"the timed clip, all {T_CLIP} frames, vs the fp32 CPU oracle",
+                          "overflow_flag": net3.overflowed()}
+            if fp32_grade["max_abs"] > 1e-4:
+                parity["ok"] = False
+            del net3, y3, d3
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            fp32_grade = {"unavailable": f"{type(e).__name__}: {e}"}
     del ref
 
     gpu_ref, cpu, stream100 = None, None, None
@@ -652,6 +681,7 @@ def run_b200(args):
         "gpu_reference": gpu_ref,
         "cpu_baseline": cpu,
         "stream100_bf16": stream100,
+        "fp32_grade": fp32_grade,
         "workspace_bytes": int(lib.bsvd_workspace_bytes(net._handle)),
     }
     print(json.dumps(line), flush=True)
@@ -674,6 +704,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--no-fp32x3", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=40)
     ap.add_argument("--quick-parity", action="store_true", help="parity on 2 frames instead of all 10")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],

@@ -112,7 +112,9 @@ class BSVD(nn.Module):
                 self._param_names.append(f"temp{blk + 1}.{stem}")
         self.shift_num = 16          # count_shift(): 8 BiBufferConv per DenBlock (bsvd_arch.py:554-560)
         self.independent_clips = False   # True: forward([N,F,..]) treats the N clips separately
-        self.precision = precision or os.environ.get("BSVD_B200_PRECISION")  # 'fp16' | 'bf16' | None
+        # 'fp16' | 'bf16' | 'fp32x3' (fp32-grade: three fp16 tensor-core products per contraction, ~1e-5 from
+        # the fp32 reference at a third of the speed; for val.fp16 = False callers) | None = from dtype / autocast
+        self.precision = precision or os.environ.get("BSVD_B200_PRECISION")
         self._handle = None
         self._handle_prec = None
         self._handle_dev = None
@@ -160,8 +162,8 @@ class BSVD(nn.Module):
     def _select_precision(self):
         if self.precision is not None:
             p = str(self.precision).lower()
-            if p not in ("fp16", "bf16"):
-                raise ValueError("precision must be 'fp16' or 'bf16'")
+            if p not in ("fp16", "bf16", "fp32x3"):
+                raise ValueError("precision must be 'fp16', 'bf16' or 'fp32x3'")
             return p
         w = self._first_weight()
         if w.dtype == torch.bfloat16:
@@ -197,7 +199,7 @@ class BSVD(nn.Module):
             cfg.mid_ch, cfg.interm_ch = self.cfg["mid_ch"], self.cfg["interm_ch"]
             cfg.in_ch, cfg.out_ch = self.cfg["in_ch"], self.cfg["out_ch"]
             cfg.act_relu6, cfg.norm_none = (1 if self.cfg["act"] == "relu6" else 0), 1
-            cfg.precision = capi.PREC_FP16 if prec == "fp16" else capi.PREC_BF16
+            cfg.precision = {"fp16": capi.PREC_FP16, "bf16": capi.PREC_BF16, "fp32x3": capi.PREC_FP32X3}[prec]
             cfg.device = dev_index
             h = C.c_void_p()
             capi.check(lib.bsvd_create(C.byref(cfg), C.byref(h)))

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BSVD_B200_LIB") or os.path.join(_HERE, "lib", "libbsvd_b200.so")
 
 NUM_LAYERS = 32
-PREC_FP16, PREC_BF16 = 0, 1
+PREC_FP16, PREC_BF16, PREC_FP32X3 = 0, 1, 2
 EPI_RELU6, EPI_PIXSHUF, EPI_SKIP_ADD, EPI_SHIFT_STORE, EPI_STRIDE2 = 1, 2, 4, 8, 16
 
 # every symbol include/bsvd_b200.h declares (tests check that the library exports all of them)

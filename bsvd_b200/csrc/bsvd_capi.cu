@@ -21,6 +21,7 @@
 #include "final_conv.cuh"
 #include "first_conv.cuh"
 #include "metrics.cuh"
+#include "split_edge.cuh"
 
 namespace bsvd {
 
@@ -175,6 +176,18 @@ static uint16_t f32_to_f16(float f) {
   return (uint16_t)(sign | (base + q));
 }
 static inline uint16_t to16(float f, int bf16) { return bf16 ? f32_to_bf16(f) : f32_to_f16(f); }
+static float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t u;
+  if (e == 0) {
+    if (m == 0) u = sign;
+    else { int sh = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++sh; } u = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 0x3ffu) << 13); }
+  } else if (e == 31) u = sign | 0x7f800000u | (m << 13);
+  else u = sign | ((e + 112) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 
 // ------------------------------------------------------------------------------------------------
 // one fused conv stage: static description + packed weights + launch
@@ -197,6 +210,10 @@ struct StageSpec {
   bool pair_s2 = false;     // stride-2 conv reading pairs (conv_tc.cuh PIPE 5): 6 (dy, pair) taps
   bool pair_final = false;  // last conv (32 -> 3) on pairs (final_conv.cuh PAIR instances)
   int store_c = 0;          // first conv: channels actually stored when fewer than the GEMM's 64 columns
+  // fp32-grade mode (BSVD_PREC_FP32X3, ConvParams::phys_chunks): activations stored as [hi(C) | lo(C)] fp16,
+  // K walks [x_hi | x_lo | x_hi] against [W_hi | W_hi | W_lo]; the first / last conv run in fp32 on the CUDA
+  // cores (split_edge.cuh)
+  bool split = false;
   // derived
   int gemm_n = 64, ntile = 64, rows = 2, cin_chunks = 1, tap_begin = 0, tap_end = 9;
   void derive() {
@@ -213,13 +230,16 @@ struct StageSpec {
     static const int stack_on = [] { const char* e = getenv("BSVD_B200_STACK"); return e ? atoi(e) : 1; }();
     static const int cta2_on = [] { const char* e = getenv("BSVD_B200_NO_CTA2"); return (e && e[0] == '1') ? 0 : 1; }();
     stacked = stack_on && cta2_on && cin == 64 && cout == 64 && stride == 1 && !first_im2col &&
-              !final_out && !pixshuf && !skip;
+              !final_out && !pixshuf && !skip && !split;
+    if (split && !first_im2col && !final_out) cin_chunks = 3 * cin / kChunk;     // virtual chunks
     if (stacked) { tap_begin = 0; tap_end = 3; }   // three dx slabs of [192 rows per CTA][64]
     if (pair_s2) { tap_begin = 0; tap_end = 6; }
   }
   int ntaps() const { return tap_end - tap_begin; }
   int n_tiles() const { return gemm_n / ntile; }
   size_t pack_elems() const {
+    if (split && first_im2col) return (size_t)64 * 4 * 9 * 2;     // fp32 [64][4][9] (counted in 16-bit units)
+    if (split && final_out) return (size_t)3 * 64 * 9 * 2;        // fp32 [3][64][9]
     if (pair_final) return (size_t)3 * kFinalNPair * kChunk;   // [pair tap][dy*8+a*4+co][64]
     if (final_out) return (size_t)3 * kFinalN * kChunk;   // [dx][dy*3+co][64]
     if (stacked) return (size_t)3 * 2 * 192 * kChunk;     // [dx][cta rank][192 rows][64]
@@ -240,6 +260,46 @@ static inline int col_to_cout(const StageSpec& s, int col) {
 // its eight 16-byte chunks XOR-swizzled by (row & 7) (SWIZZLE_128B K-major canonical layout).
 static void pack_weights(const StageSpec& s, const float* w, const float* b, int bf16,
                          std::vector<uint16_t>& pack, std::vector<float>& bias) {
+  if (s.split && (s.first_im2col || s.final_out)) {
+    // fp32 weights for the CUDA-core edge convs (split_edge.cuh)
+    pack.assign(s.pack_elems(), 0);
+    float* wf = reinterpret_cast<float*>(pack.data());
+    if (s.first_im2col) {
+      bias.assign(64, 0.f);
+      for (int co = 0; co < s.cout_l; ++co) {
+        bias[co] = b ? b[co] : 0.f;
+        for (int ci = 0; ci < s.cin_l && ci < 4; ++ci)
+          for (int t = 0; t < 9; ++t) wf[(co * 4 + ci) * 9 + t] = w[((size_t)co * s.cin_l + ci) * 9 + t];
+      }
+    } else {
+      bias.assign(16, 0.f);
+      for (int co = 0; co < s.cout_l; ++co) {
+        bias[co] = b ? b[co] : 0.f;
+        for (int ci = 0; ci < s.cin_l && ci < 64; ++ci)
+          for (int t = 0; t < 9; ++t) wf[(co * 64 + ci) * 9 + t] = w[((size_t)co * s.cin_l + ci) * 9 + t];
+      }
+    }
+    return;
+  }
+  if (s.split && s.cin_chunks == 3 * s.cin / kChunk && s.cin_l <= s.cin) {
+    // [W_hi | W_hi | W_lo] over the virtual input channels [x_hi | x_lo | x_hi]; every entry is exactly
+    // representable in fp16, so the 16-bit packing below is lossless
+    const int C = s.cin;
+    std::vector<float> w3((size_t)s.cout_l * 3 * C * 9, 0.f);
+    for (int co = 0; co < s.cout_l; ++co)
+      for (int ci = 0; ci < s.cin_l; ++ci)
+        for (int t = 0; t < 9; ++t) {
+          const float v = w[((size_t)co * s.cin_l + ci) * 9 + t];
+          const float hi = f16_to_f32(f32_to_f16(v)), lo = f16_to_f32(f32_to_f16(v - hi));
+          w3[((size_t)co * 3 * C + ci) * 9 + t] = hi;
+          w3[((size_t)co * 3 * C + C + ci) * 9 + t] = hi;
+          w3[((size_t)co * 3 * C + 2 * C + ci) * 9 + t] = lo;
+        }
+    StageSpec d = s;
+    d.split = false; d.cin = 3 * C; d.cin_l = 3 * C;          // plain stage with 3C input channels
+    pack_weights(d, w3.data(), b, 0, pack, bias);
+    return;
+  }
   if (s.pairx) {
     // expand to the dense 64 -> 64 pair conv and pack that like any other 64 -> 64 stage
     std::vector<float> wp((size_t)64 * 64 * 9, 0.f), bp(64, 0.f);
@@ -453,9 +513,11 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   // (upc2.convblock.0, with its temporal shift, keeps the skip add in the epilogue unless
   // BSVD_B200_SKIP_MMA_SHIFT=1: its MMA time is the bound, not its epilogue)
   static const int up_shift_on = [] { const char* e = getenv("BSVD_B200_SKIP_MMA_SHIFT"); return (e && e[0] == '1') ? 1 : 0; }();
-  const bool skip_mma = up_on && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
-                        !s.first_im2col && !s.final_out && (!s.shift || up_shift_on) &&
-                        s.cin_chunks * s.ntaps() >= 4 * (s.ntile / 64);   // one skip block per four slabs
+  const int skip_blocks = s.ntile / 64 * (s.split ? 2 : 1);      // split: hi and lo halves of the skip tensor
+  const bool skip_mma = (up_on || s.split) && cta2 && s.skip && s.pixshuf && s.ntile == 256 && s.rows == 1 &&
+                        !s.first_im2col && !s.final_out && (!s.shift || up_shift_on || s.split) &&
+                        s.cin_chunks * s.ntaps() >= 4 * skip_blocks;   // one skip block per four slabs
+  if (s.split && s.skip && !skip_mma) return fail("fp32-grade mode: the skip add of this stage must run on the tensor core");
   static const int tma_on = [] { const char* e = getenv("BSVD_B200_NO_TMA_OUT"); return (e && e[0] == '1') ? 0 : 1; }();
   static const int tma_shift_on = [] { const char* e = getenv("BSVD_B200_TMA_SHIFT"); return e ? atoi(e) : 0; }();   // measured: -3 % when on
   const bool tma_out = tma_on && cta2 && (!s.shift || (tma_shift_on && !s.pixshuf)) &&
@@ -463,7 +525,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
                        !s.final_out && !(desc_variant & ~(2 | 4 | 16 | 128));
   // two staging tiles per warp when they fit; the stacked 64->64 stages (resident 72 KB bank) have
   // room for one, whose TMA read is awaited right before it is rewritten
-  const int stg_bufs = (tma_out && !s.stacked) ? 2 : 1;
+  const int stg_bufs = ((tma_out && !s.stacked) || s.split) ? 2 : 1;   // split: hi and lo tiles
   const size_t kStagingBytes = staging_bytes(L->ew) * stg_bufs + (skip_mma ? 4096 : 0);
   const int Ho = io.H / s.stride, Wo = io.W / s.stride;
   if (s.stride == 2 && ((io.H & 1) || (io.W & 1))) return fail("stride-2 stage needs even H, W");
@@ -475,6 +537,22 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.tap_begin = s.tap_begin; p.tap_end = s.tap_end;
   p.xblocks = (Wo + kRunPx - 1) / kRunPx;
   p.yblocks = (Ho + s.rows - 1) / s.rows;
+  L->split = s.split ? 1 : 0;
+  p.out_pitch_C = 0;
+  if (s.split && (s.first_im2col || s.final_out)) {
+    // fp32 CUDA-core edge convs of the fp32-grade mode (split_edge.cuh): one thread per pixel
+    p.wpack = sd.wpack; p.bias = sd.bias;
+    p.flags = s.first_im2col ? (s.relu ? EPI_RELU : EPI_RELU6) : EPI_FINAL;
+    p.out = io.out; p.skip = io.skip;
+    if (s.final_out && !io.skip) return fail("stage needs a skip tensor");
+    L->first_in = nullptr;
+    L->in_ptr = io.in;
+    L->cta2 = 0;
+    L->map = CUtensorMap(); L->map_w = L->map; L->map_s = L->map; L->map_o = L->map; L->map_raw = L->map; L->map_rawnm = L->map;
+    L->grid = 0; L->smem = 0;
+    L->ntile = s.first_im2col ? -2 : 18; L->rows = 1;
+    return 0;
+  }
   if (s.first_im2col) {
     // dedicated kernel (first_conv.cuh): patches are built in shared memory from the raw input
     p.n_tiles = 1;
@@ -485,6 +563,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.flags = (s.relu ? EPI_RELU : EPI_RELU6) | (bf16 ? EPI_BF16 : 0);
     const int oc = s.store_c ? s.store_c : s.cout;     // 32: only the first unit of every row is stored
     p.out = io.out; p.out_C = oc; p.out_H = Ho; p.out_W = Wo; p.out_C_log2 = (oc == 32) ? 5 : 6;
+    p.out_pitch_C = oc;
     p.out_frame_stride = (long long)Ho * Wo * oc;
     L->cta2 = 0;
     if (make_map_pix(&L->map_o, io.out, io.out_T ? io.out_T : io.T,
@@ -519,7 +598,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.positions = p.T * p.yblocks * p.xblocks;
   p.total_tiles = (cta2 ? (p.positions + 1) / 2 : p.positions) * p.n_tiles;
   p.mode = (s.stride == 2) ? 1 : 0;
-  p.cin_total = s.cin;
+  p.cin_total = s.split ? 2 * s.cin : s.cin;          // channels per pixel as stored (stride-2 column parity offset)
+  p.phys_chunks = s.split ? 2 * s.cin / kChunk : 0;
   p.w_stage_bytes = (uint32_t)s.ntile * 128u / (cta2 ? 2u : 1u);
   p.w_rows_cta = s.ntile / 2;
   const bool stacked = s.stacked;
@@ -582,7 +662,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.out = io.out; p.out_prev = io.out_prev; p.out_next = io.out_next; p.ring_mode = io.ring_mode;
   if (s.pixshuf) { p.out_C = s.cout / 4; p.out_H = 2 * Ho; p.out_W = 2 * Wo; }
   else { p.out_C = s.final_out ? 3 : s.cout; p.out_H = Ho; p.out_W = Wo; }
-  p.out_frame_stride = (long long)p.out_H * p.out_W * p.out_C;
+  p.out_pitch_C = s.split ? 2 * p.out_C : p.out_C;
+  p.out_frame_stride = (long long)p.out_H * p.out_W * p.out_pitch_C;
   p.out_C_log2 = 0;
   while ((1 << p.out_C_log2) < p.out_C) ++p.out_C_log2;
   if ((1 << p.out_C_log2) != p.out_C || p.out_C < 32) return fail("output channels must be a power of two >= 32");
@@ -591,13 +672,14 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   p.resid_in = io.resid_in; p.resid_C = io.resid_C; p.aux_out = io.aux_out;
   p.fold = p.out_C / 8;
   p.stg_bytes_per_warp = kStageBytesPerWarp * stg_bufs;
-  p.skip_mma = skip_mma ? s.ntile / 64 : 0;
+  p.skip_mma = skip_mma ? skip_blocks : 0;
+  p.skip_blocks = s.ntile / 64;
   p.tma_out = tma_out ? 1 : 0;
   if ((s.skip || s.final_out) && !io.skip) return fail("stage needs a skip tensor");
   if (s.resid_in && !io.resid_in) return fail("stage needs the raw input for the residual");
 
   // pair stride-2: the [T][H/2][2][W/2][2*32] view of the 32-channel tensor has the pairs as its pixels
-  const int cin_map = s.first_im2col ? kChunk : (s.pair_s2 ? 32 : s.cin);
+  const int cin_map = s.first_im2col ? kChunk : (s.pair_s2 ? 32 : (s.split ? 2 * s.cin : s.cin));
   int rc = (s.stride != 2) ? make_map_halo(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows)
            : (p.mode >= 4) ? make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows + 1, kS2BoxPx)
                            : make_map_s2(&L->map, io.in, io.T, io.H, io.W, cin_map, s.rows);
@@ -615,16 +697,16 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   }
   const long long frame_bytes = p.out_frame_stride * 2;
   if (skip_mma) {
-    if (p.w_stage_bytes != 16384u || p.w_resident || s.cin_chunks * s.ntaps() < 4 * (s.ntile / 64))
+    if (p.w_stage_bytes != 16384u || p.w_resident || s.cin_chunks * s.ntaps() < 4 * skip_blocks)
       return fail("skip blocks need 16 KB filter-ring slots and at least four slabs per block");
     rc = make_map_pix(&L->map_s, io.skip, io.skip_T ? io.skip_T : io.T,
-                      io.skip_T ? io.skip_T_stride : frame_bytes, p.out_H, p.out_W, p.out_C, 1, kChunk,
+                      io.skip_T ? io.skip_T_stride : frame_bytes, p.out_H, p.out_W, p.out_pitch_C, 1, kChunk,
                       kRunPx, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   if (tma_out) {
     rc = make_map_pix(&L->map_o, io.out, io.out_T ? io.out_T : io.T, io.out_T ? io.out_T_stride : frame_bytes,
-                      p.out_H, p.out_W, p.out_C, s.pixshuf ? 1 : 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+                      p.out_H, p.out_W, p.out_pitch_C, s.pixshuf ? 1 : 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   L->grid = cta2 ? 2 * std::min(p.total_tiles, num_sms() / 2) : std::min(p.total_tiles, num_sms());
@@ -669,6 +751,25 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
 }
 
 static int launch_stage(const StageLaunch& L, cudaStream_t st) {
+  if (L.ntile == -2 || L.ntile == 18) {
+    // fp32-grade mode, first / last conv on the CUDA cores (split_edge.cuh)
+    const ConvParams& p = L.p;
+    const dim3 grid((p.W + kEdgeThreads - 1) / kEdgeThreads, p.H, p.T);
+    if (L.ntile == -2) {
+      if (!L.first_in) return fail("first stage launched without an input pointer");
+      if (L.first_u8) return fail("fp32-grade mode: uint8 frame input is not implemented");
+      first_conv_split_kernel<<<grid, kEdgeThreads, 0, st>>>(
+          L.first_in, L.first_nmap, L.first_inc, reinterpret_cast<const float*>(p.wpack), p.bias,
+          reinterpret_cast<uint16_t*>(p.out), p.T, p.H, p.W, p.src_H, p.src_W, p.use_sigma, p.sigma_const,
+          (p.flags & EPI_RELU6) ? 1 : 0);
+    } else {
+      final_conv_split_kernel<<<grid, kEdgeThreads, 0, st>>>(
+          reinterpret_cast<const uint16_t*>(L.in_ptr), reinterpret_cast<const float*>(p.wpack), p.bias,
+          reinterpret_cast<const float*>(p.skip), p.out, p.T, p.H, p.W, p.src_H, p.src_W, p.clamp01, p.out_u8, p.u8_bgr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   if (L.ntile == -1) return launch_first(L, st);
   if (L.ntile == 16 || L.ntile == 17) {
     static std::atomic<bool> attr_done[64];
@@ -752,6 +853,7 @@ struct bsvd_handle {
   bsvd_config cfg;
   int bf16 = 0;
   int pair32 = 0;               // c32 configurations in their native layout (32 channels at full resolution)
+  int split = 0;                // fp32-grade mode: every activation tensor holds [hi | lo], 2x the channels below
   int cp[3] = {64, 128, 256};   // channels of the full / half / quarter resolution tensors as stored
   StageDev stages[BSVD_NUM_LAYERS];
   // ---- clip-mode workspace / plan (rebuilt when T,H,W change) ----
@@ -882,6 +984,8 @@ static void build_specs(bsvd_handle* h) {
     set(15, c0, out_ch, false);
     S(15).resid_in = (blk == 0); S(15).final_out = (blk == 1);
     if (blk == 1) S(15).cout = out_ch;                                // 3 output planes, no padding
+    if (h->split)
+      for (int l = 0; l < 16; ++l) S(l).split = true;
     if (h->pair32) {
       // native layout of the c32 configurations (see StageSpec::pairx): full-resolution tensors hold 32
       // channels per pixel and are processed as pixel pairs; nothing below full resolution is padded
@@ -897,6 +1001,8 @@ static void build_specs(bsvd_handle* h) {
   }
   h->cp[0] = h->pair32 ? 32 : pad64(h->cfg.chns[0]);
   h->cp[1] = pad64(h->cfg.chns[1]); h->cp[2] = pad64(h->cfg.chns[2]);
+  if (h->split)            // [hi | lo]: twice the channels per pixel in every activation tensor
+    for (int i = 0; i < 3; ++i) h->cp[i] *= 2;
 }
 
 extern "C" { static void free_stream(bsvd_handle* h); }
@@ -918,7 +1024,7 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     const size_t half = (size_t)T * (H / 2) * (W / 2) * h->cp[1] * 2;
     const size_t quar = (size_t)T * (H / 4) * (W / 4) * h->cp[2] * 2;
     const size_t fa = align_up(full, 1024), ha = align_up(half, 1024), qa = align_up(quar, 1024);
-    const size_t sa = align_up((size_t)T * H * W * 4 * 2, 1024);
+    const size_t sa = align_up((size_t)T * H * W * 4 * (h->split ? 4 : 2), 1024);   // compact skip1 copy (fp32 when split)
     h->ws_bytes = 4 * fa + 3 * ha + 2 * qa + sa;
     CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
     uint8_t* b = reinterpret_cast<uint8_t*>(h->ws);
@@ -962,10 +1068,11 @@ static int build_clip_plan(bsvd_handle* h, const float* in, const float* nmap, f
     rc |= plan(7, h->bufQ1, H4, W4, h->bufQ0);
     rc |= plan(8, h->bufQ0, H4, W4, h->bufQ1);
     rc |= plan(9, h->bufQ1, H4, W4, h->bufQ0);
-    rc |= plan(10, h->bufQ0, H4, W4, h->bufH0, h->bufX1, h->cp[1], fs_half);
+    const int lc0 = h->split ? h->cp[0] / 2 : h->cp[0], lc1 = h->split ? h->cp[1] / 2 : h->cp[1];   // logical channels
+    rc |= plan(10, h->bufQ0, H4, W4, h->bufH0, h->bufX1, lc1, fs_half);
     rc |= plan(11, h->bufH0, H2, W2, h->bufH1);
     rc |= plan(12, h->bufH1, H2, W2, h->bufH0);
-    rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, h->cp[0], fs_full);
+    rc |= plan(13, h->bufH0, H2, W2, h->bufA, h->bufX0, lc0, fs_full);
     rc |= plan(14, h->bufA, H, W, h->bufP);
     if (blk == 0) rc |= plan(15, h->bufP, H, W, h->bufM);
     else rc |= plan(15, h->bufP, H, W, out, h->bufS, 4, (long long)H * W * 4);
@@ -1007,8 +1114,10 @@ int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
                 "[32,64,128] (options/train/0402_*_c32.yml, zero-padded to the 64-channel kernels), "
                 "mid_ch<=64, interm_ch<=64, in_ch=4 (or 3 = blind), out_ch=3, norm='none', "
                 "act='relu6'|'relu'; there is no CPU fallback");
-  if (cfg->precision != BSVD_PREC_FP16 && cfg->precision != BSVD_PREC_BF16)
+  if (cfg->precision != BSVD_PREC_FP16 && cfg->precision != BSVD_PREC_BF16 && cfg->precision != BSVD_PREC_FP32X3)
     return fail("unknown precision %d", cfg->precision);
+  if (cfg->precision == BSVD_PREC_FP32X3 && !(c64 && cfg->act_relu6 == 1))
+    return fail("the fp32-grade mode (BSVD_PREC_FP32X3) implements the BSVD-64 configuration (options/test/bsvd_c64.yml)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("no CUDA device: this library only runs on a B200 (sm_100a); no CPU fallback");
@@ -1021,6 +1130,7 @@ int bsvd_create(const bsvd_config* cfg, bsvd_handle** out) {
   h->cfg = *cfg;
   h->device = dev;
   h->bf16 = (cfg->precision == BSVD_PREC_BF16);
+  h->split = (cfg->precision == BSVD_PREC_FP32X3) ? 1 : 0;
   {
     // BSVD_B200_C32_PADDED=1: the round-1 path (every channel count below 64 zero-padded to 64)
     const char* e = getenv("BSVD_B200_C32_PADDED");
@@ -1454,7 +1564,7 @@ static int build_stream(bsvd_handle* h, int H, int W) {
     for (int k = 0; k < kNumRings; ++k) total += ring_slot_bytes(h, k, H, W) * kRingSlots[k];
   const size_t raw_bytes = align_up((size_t)9 * 4 * H * W * sizeof(float), 1024);
   total += raw_bytes;
-  const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+  const size_t aux_slot = align_up((size_t)H * W * 4 * (h->split ? 4 : 2), 1024);
   total += 9 * aux_slot;
   const size_t out_bytes = align_up((size_t)3 * H * W * sizeof(float), 1024);
   total += out_bytes;
@@ -1484,11 +1594,11 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       io.ring_mode = sd.spec.shift ? 1 : 0;
       io.zero_future = sd.spec.shift ? 1 : 0;
       io.out_next = io.out;                      // placeholders so plan_stage's checks pass
-      io.skip = S.ring[b][kRingX0]; io.skip_C = h->cp[0];
+      io.skip = S.ring[b][kRingX0]; io.skip_C = h->split ? h->cp[0] / 2 : h->cp[0];
       io.resid_in = S.raw; io.resid_C = 4;
       io.skip_T = kRingSlots[kRingX0]; io.skip_T_stride = (long long)ring_slot_bytes(h, kRingX0, H, W);
       if (l == 10) {
-        io.skip = S.ring[b][kRingX1]; io.skip_C = h->cp[1];
+        io.skip = S.ring[b][kRingX1]; io.skip_C = h->split ? h->cp[1] / 2 : h->cp[1];
         io.skip_T = kRingSlots[kRingX1]; io.skip_T_stride = (long long)ring_slot_bytes(h, kRingX1, H, W);
       }
       io.out_T = kRingSlots[kLayerOut[l]]; io.out_T_stride = (long long)ring_slot_bytes(h, kLayerOut[l], H, W);
@@ -1497,7 +1607,8 @@ static int build_stream(bsvd_handle* h, int H, int W) {
       if (plan_stage(sd, io, h->bf16, 0, &SL.tmpl)) return 1;
       const int nslots = kRingSlots[in_ring];
       SL.maps.resize(nslots);
-      const int cin_map = sd.spec.first_im2col ? kChunk : (sd.spec.pair_s2 ? 32 : sd.spec.cin);
+      const int cin_map = sd.spec.first_im2col ? kChunk
+                          : (sd.spec.pair_s2 ? 32 : (sd.spec.split ? 2 * sd.spec.cin : sd.spec.cin));   // channels per pixel as stored
       if (b == 0 && l == 0 && raw_tma_ok(S.raw, nullptr, W)) {
         SL.raw_maps.resize(9);
         for (int k = 0; k < 9; ++k)
@@ -1552,7 +1663,7 @@ static int run_stream_layers(bsvd_handle* h, long long s, long long F, cudaStrea
         p.skip_t0 = (int)(f % kRingSlots[kRingX0]);
         p.skip = S.ring[b][kRingX0] + (size_t)p.skip_t0 * ring_slot_bytes(h, kRingX0, H, W);
       }
-      const size_t aux_slot = align_up((size_t)H * W * 4 * 2, 1024);
+      const size_t aux_slot = align_up((size_t)H * W * 4 * (h->split ? 4 : 2), 1024);
       if (l == 0 && b == 0) {
         L.first_in = S.raw + (size_t)(f % 9) * 4 * plane;   // raw ring slot holds all 4 channels
         L.first_nmap = nullptr; L.first_inc = h->cfg.in_ch;   // blind model: planes 0..2 only

@@ -97,7 +97,8 @@ enum : int {
   EPI_BF16 = 64,        // 16-bit storage type is bf16 (else fp16)
   EPI_ZERO_FUTURE = 128, // streaming: always zero own [0:fold) (overwritten when t+1 arrives)
   EPI_TMA_OUT = 256,    // compile-time only: units leave through cp.async.bulk.tensor stores
-  EPI_RELU = 512        // nn.ReLU (act='relu', the c32 configurations) instead of nn.ReLU6
+  EPI_RELU = 512,       // nn.ReLU (act='relu', the c32 configurations) instead of nn.ReLU6
+  EPI_SPLIT = 1024      // compile-time only: fp32-grade mode, every stored value leaves as a (hi, lo) fp16 pair
 };
 
 struct ConvParams {
@@ -171,6 +172,13 @@ struct ConvParams {
   // residual / compact-copy code of temp1's last conv needs to know (EPI_RESID_IN).
   int pair_px;
   int seg_T;            // clip mode: frames per independent clip when the T frames are several clips (0 = one clip)
+  // ---- fp32-grade mode (BSVD_PREC_FP32X3): x = hi + lo, W = hi + lo in fp16, y = W_hi x_hi + W_hi x_lo + W_lo x_hi.
+  // A tensor with C logical channels is stored with 2C channels per pixel, [hi(C) | lo(C)]; the K loop walks
+  // 3C "virtual" input channels [x_hi | x_lo | x_hi] against the packed weights [W_hi | W_hi | W_lo]:
+  // virtual chunk c reads physical chunk c % phys_chunks.  The epilogue stores hi at channel n, lo at n + out_C.
+  int phys_chunks;      // physical 64-channel chunks per pixel of the input tensor (0 = cin_chunks: no wrap)
+  int out_pitch_C;      // channels per pixel of the OUTPUT tensor as stored (out_C, or 2 * out_C in split mode)
+  int skip_blocks;      // skip_mma: blocks per accumulator set (= skip_mma without split; skip_mma = 2x with it)
 };
 // reflected source coordinate of padded coordinate v (v < n_pad), source extent n (bottom/right pad)
 __device__ __forceinline__ int reflect_src(int v, int n) { return v < n ? v : 2 * n - 2 - v; }
@@ -508,7 +516,8 @@ __device__ __forceinline__ uint32_t relu6_packed(uint32_t u) {
 // kernel parameter bank; re-reading it per unit costs constant-cache latency on the epilogue's
 // critical path).  skip_prefetch / epilogue_unit are duck-typed on it.
 struct EpiParams {
-  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0, pair_px, seg_T;
+  int flags, T, H, W, out_C, out_W, out_C_log2, fold, ring_mode, skip_C, resid_C, desc_variant, out_t0, pair_px, seg_T,
+      out_pitch_C;
   uint32_t stg_bytes_per_warp;
   int src_H, src_W;
   void* out; void* out_prev; void* out_next; void* aux_out;
@@ -519,7 +528,7 @@ struct EpiParams {
       : flags(p.flags), T(p.T), H(p.H), W(p.W), out_C(p.out_C), out_W(p.out_W),
         out_C_log2(p.out_C_log2), fold(p.fold),
         ring_mode(p.ring_mode), skip_C(p.skip_C), resid_C(p.resid_C), desc_variant(p.desc_variant),
-        out_t0(p.out_t0), pair_px(p.pair_px), seg_T(p.seg_T), stg_bytes_per_warp(p.stg_bytes_per_warp),
+        out_t0(p.out_t0), pair_px(p.pair_px), seg_T(p.seg_T), out_pitch_C(p.out_pitch_C), stg_bytes_per_warp(p.stg_bytes_per_warp),
         src_H(p.src_H ? p.src_H : p.H), src_W(p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W)),
         out(p.out), out_prev(p.out_prev), out_next(p.out_next), aux_out(p.aux_out), skip(p.skip),
         resid_in(p.resid_in), overflow(p.overflow), out_frame_stride(p.out_frame_stride),
@@ -540,10 +549,10 @@ __device__ __forceinline__ UnitPos unit_pos(const P& p, const TileCoord& tc, int
   if (((MASK & EPI_PIXSHUF) != 0) && (p.flags & EPI_PIXSHUF)) {
     const int q = nbase >> p.out_C_log2;
     u.cb = nbase & (p.out_C - 1);
-    u.base = (static_cast<long long>(2 * y + (q >> 1)) * p.out_W + 2 * xb + (q & 1)) * p.out_C + u.cb;
+    u.base = (static_cast<long long>(2 * y + (q >> 1)) * p.out_W + 2 * xb + (q & 1)) * p.out_pitch_C + u.cb;
   } else {
     u.cb = nbase;
-    u.base = (static_cast<long long>(y) * p.out_W + xb) * p.out_C + u.cb;
+    u.base = (static_cast<long long>(y) * p.out_W + xb) * p.out_pitch_C + u.cb;
   }
   return u;
 }
@@ -559,8 +568,8 @@ template <int MASK, class P>
 __device__ __forceinline__ EpiLane epi_lane(const P& p, int lane) {
   EpiLane l;
   const bool ps = ((MASK & EPI_PIXSHUF) != 0) && (p.flags & EPI_PIXSHUF);
-  l.off = static_cast<uint32_t>((ps ? 2 : 1) * (lane >> 2) * p.out_C + 8 * (lane & 3));
-  l.step = static_cast<uint32_t>((ps ? 16 : 8) * p.out_C);
+  l.off = static_cast<uint32_t>((ps ? 2 : 1) * (lane >> 2) * p.out_pitch_C + 8 * (lane & 3));
+  l.step = static_cast<uint32_t>((ps ? 16 : 8) * p.out_pitch_C);
   l.nvalid = 0;
   return l;
 }
@@ -584,124 +593,17 @@ __device__ __forceinline__ void skip_prefetch(const P& p, const TileCoord& tc, c
 }
 
 // MASK = set of EPI_* features compiled into this instance (runtime flags are a subset of it).
+// Store phase of one unit: park the lane's 64 bytes in the staging tile, then either one TMA store of the
+// tile or the transposed read-back with 128-bit global stores routed to frame t-1 / t / t+1.  `coff` is
+// the channel offset of this piece inside the pixel (0, or out_C for the lo half in split mode).
 template <bool BF16, int MASK, class P>
-__device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, const EpiLane& el, int y,
-                                              int nbase, const uint32_t (&v)[32],
-                                              const uint4 (&sk)[4],
-                                              const float (&bv)[32], uint32_t stg, int quad,
-                                              int lane, const float (&rin)[3], bool use_rin,
-                                              const CUtensorMap* map_o = nullptr) {
+__device__ __forceinline__ void epilogue_emit(const P& p, const TileCoord& tc, const EpiLane& el, int y, int nbase,
+                                              const uint4 (&o)[4], uint32_t stg, int quad, int lane, int coff,
+                                              const CUtensorMap* map_o) {
   const int flags = p.flags & MASK;
-
-  // ------------------------------ phase 0 ------------------------------
-  // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
-  if constexpr ((MASK & EPI_SKIP) != 0) {
-    if (flags & EPI_SKIP) {
-      const int j = lane & 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pl = 8 * i + (lane >> 2);
-        const uint32_t a = stg + pl * 64 + ((j ^ ((pl >> 1) & 3)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(sk[i].x), "r"(sk[i].y),
-                     "r"(sk[i].z), "r"(sk[i].w) : "memory");
-      }
-      __syncwarp();
-    }
-  }
-  // ------------------------------ phase 1 ------------------------------
-  // (shared-memory accesses are batched: all loads of a phase are issued before their first use)
   {
-    const int x = tc.x0 + quad * 32 + lane;
-    const bool valid = (lane < el.nvalid) && (y < p.H);
     const uint32_t row = stg + lane * 64;
     const uint32_t swz = (lane >> 1) & 3;
-    uint4 sv[4];
-    bool add_skip = false;
-    if constexpr ((MASK & EPI_SKIP) != 0) {
-      add_skip = (flags & EPI_SKIP) && valid;
-      if (flags & EPI_SKIP) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(sv[j].x), "=r"(sv[j].y), "=r"(sv[j].z), "=r"(sv[j].w)
-                       : "r"(row + ((j ^ swz) << 4)) : "memory");
-      }
-    }
-    uint4 o[4];
-    // range guard: running maximum of what this lane stores (|x|, or x under ReLU, which clamps the
-    // negative side); ReLU6 stages are bounded and skip it
-    const bool chk_range = !BF16 && !(flags & EPI_RELU6) && p.overflow != nullptr;
-    const bool chk_signed = (flags & EPI_RELU) != 0;
-    float vmax = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float f[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) + bv[8 * j + i];
-      if constexpr ((MASK & EPI_SKIP) != 0) {
-        if (add_skip) {
-          const float2 a = unpack2<BF16>(sv[j].x), b = unpack2<BF16>(sv[j].y),
-                       c = unpack2<BF16>(sv[j].z), d = unpack2<BF16>(sv[j].w);
-          f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
-          f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
-        }
-      }
-      if constexpr ((MASK & EPI_RESID_IN) != 0) {
-        // pair mode: unit 0 / 1 of a row hold pixel 2x / 2x+1, each with its own channels 0..2
-        const bool resid_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
-        if ((flags & EPI_RESID_IN) && j == 0 && resid_unit && valid) {
-          // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
-          if (use_rin) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) f[i] = rin[i] - f[i];
-          } else {
-            const int xr = p.pair_px ? 2 * x + (nbase >> 5) : x;
-            const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W);
-            const long long plane = static_cast<long long>(sH) * sW;
-            const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
-                             static_cast<long long>(reflect_src(y, sH)) * sW + reflect_src(xr, sW);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
-          }
-        }
-      }
-      if constexpr (!BF16) {
-        if (chk_range) {
-          if (chk_signed) {
-            vmax = fmaxf(fmaxf(vmax, f[0]), fmaxf(f[1], f[2]));
-            vmax = fmaxf(fmaxf(vmax, f[3]), fmaxf(f[4], f[5]));
-            vmax = fmaxf(vmax, fmaxf(f[6], f[7]));
-          } else {
-            vmax = fmaxf(fmaxf(vmax, fabsf(f[0])), fmaxf(fabsf(f[1]), fabsf(f[2])));
-            vmax = fmaxf(fmaxf(vmax, fabsf(f[3])), fmaxf(fabsf(f[4]), fabsf(f[5])));
-            vmax = fmaxf(vmax, fmaxf(fabsf(f[6]), fabsf(f[7])));
-          }
-        }
-      }
-      o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
-      o[j].z = pack2<BF16>(f[4], f[5]); o[j].w = pack2<BF16>(f[6], f[7]);
-      if constexpr ((MASK & EPI_RESID_IN) != 0) {
-        const bool aux_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
-        if ((flags & EPI_RESID_IN) && j == 0 && aux_unit && valid && p.aux_out) {
-          const long long pix = p.pair_px
-              ? (static_cast<long long>(tc.t) * p.H + y) * (2 * p.W) + 2 * x + (nbase >> 5)
-              : (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
-          reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o[j].x, o[j].y);
-        }
-      }
-      if (flags & EPI_RELU6) {
-        o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
-        o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
-      } else if (flags & EPI_RELU) {
-        o[j].x = relu_packed<BF16>(o[j].x); o[j].y = relu_packed<BF16>(o[j].y);
-        o[j].z = relu_packed<BF16>(o[j].z); o[j].w = relu_packed<BF16>(o[j].w);
-      }
-    }
-    if constexpr (!BF16) {
-      // fp16 range guard (see ConvParams::overflow): a value that rounds to inf (|x| >= 65520).  A NaN can
-      // only come from an inf stored by an earlier stage, which raised the (sticky) flag there.
-      if (chk_range && __any_sync(0xffffffffu, valid && !(vmax < 65520.f)) && lane == 0) atomicOr(p.overflow, 1u);
-    }
     if constexpr ((MASK & EPI_TMA_OUT) != 0) {
       // the TMA store that last read this staging tile (the previous unit's, or with two tiles per
       // warp the one before) must have drained it; awaited as late as possible
@@ -733,10 +635,10 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
     __syncwarp();
     if (lane == 0) {
       if (el.nvalid > 0 && !(p.desc_variant & 128)) {
-        int c0 = nbase, c2 = y;
+        int c0 = nbase + coff, c2 = y;
         if (p.flags & EPI_PIXSHUF) {
           const int q = nbase >> p.out_C_log2;
-          c0 = (q & 1) * p.out_C + (nbase & (p.out_C - 1));
+          c0 = (q & 1) * p.out_pitch_C + (nbase & (p.out_C - 1)) + coff;
           c2 = 2 * y + (q >> 1);
         }
         tma_store_4d(map_o, stg, c0, tc.x0 + quad * 32, c2, tc.t + p.out_t0);
@@ -783,16 +685,16 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
         }
       }
     }
-    const long long off0 = up.base + el.off;
+    const long long off0 = up.base + el.off + coff;
     const bool row_ok = (y < p.H) && !(p.desc_variant & 128);
     const int pg = lane >> 2;
     const uint32_t a0 = stg + pg * 64;
-    uint4 o[4];
+    uint4 ob[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pl = 8 * i + pg;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(o[i].x), "=r"(o[i].y), "=r"(o[i].z), "=r"(o[i].w)
+                   : "=r"(ob[i].x), "=r"(ob[i].y), "=r"(ob[i].z), "=r"(ob[i].w)
                    : "r"(a0 + i * 512 + ((j ^ ((pl >> 1) & 3)) << 4)) : "memory");
     }
     if (dst) dst += off0;
@@ -802,7 +704,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (row_ok && pg + 8 * i < el.nvalid) {
-        if (dst) *reinterpret_cast<uint4*>(dst + i * el.step) = o[i];
+        if (dst) *reinterpret_cast<uint4*>(dst + i * el.step) = ob[i];
         if constexpr ((MASK & EPI_SHIFT) != 0) {
           if (zdst) *reinterpret_cast<uint4*>(zdst + i * el.step) = make_uint4(0, 0, 0, 0);
         }
@@ -810,6 +712,157 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
     }
   }
   __syncwarp();
+}
+
+// MASK = set of EPI_* features compiled into this instance (runtime flags are a subset of it).
+template <bool BF16, int MASK, class P>
+__device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, const EpiLane& el, int y,
+                                              int nbase, const uint32_t (&v)[32],
+                                              const uint4 (&sk)[4],
+                                              const float (&bv)[32], uint32_t stg, int quad,
+                                              int lane, const float (&rin)[3], bool use_rin,
+                                              const CUtensorMap* map_o = nullptr) {
+  const int flags = p.flags & MASK;
+  constexpr bool kSplit = (MASK & EPI_SPLIT) != 0;
+  static_assert(!(kSplit && BF16), "the fp32-grade split uses fp16 pieces");
+
+  // ------------------------------ phase 0 ------------------------------
+  // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
+  if constexpr ((MASK & EPI_SKIP) != 0) {
+    if (flags & EPI_SKIP) {
+      const int j = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pl = 8 * i + (lane >> 2);
+        const uint32_t a = stg + pl * 64 + ((j ^ ((pl >> 1) & 3)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(sk[i].x), "r"(sk[i].y),
+                     "r"(sk[i].z), "r"(sk[i].w) : "memory");
+      }
+      __syncwarp();
+    }
+  }
+  // ------------------------------ phase 1 ------------------------------
+  // (shared-memory accesses are batched: all loads of a phase are issued before their first use)
+  uint4 o[4];
+  uint4 olo[kSplit ? 4 : 1];
+  {
+    const int x = tc.x0 + quad * 32 + lane;
+    const bool valid = (lane < el.nvalid) && (y < p.H);
+    const uint32_t row = stg + lane * 64;
+    const uint32_t swz = (lane >> 1) & 3;
+    uint4 sv[4];
+    bool add_skip = false;
+    if constexpr ((MASK & EPI_SKIP) != 0) {
+      add_skip = (flags & EPI_SKIP) && valid;
+      if (flags & EPI_SKIP) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(sv[j].x), "=r"(sv[j].y), "=r"(sv[j].z), "=r"(sv[j].w)
+                       : "r"(row + ((j ^ swz) << 4)) : "memory");
+      }
+    }
+    // range guard: running maximum of what this lane stores (|x|, or x under ReLU, which clamps the
+    // negative side); ReLU6 stages are bounded and skip it
+    const bool chk_range = !BF16 && !(flags & EPI_RELU6) && p.overflow != nullptr;
+    const bool chk_signed = (flags & EPI_RELU) != 0;
+    float vmax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]) + bv[8 * j + i];
+      if constexpr ((MASK & EPI_SKIP) != 0) {
+        if (add_skip) {
+          const float2 a = unpack2<BF16>(sv[j].x), b = unpack2<BF16>(sv[j].y),
+                       c = unpack2<BF16>(sv[j].z), d = unpack2<BF16>(sv[j].w);
+          f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+          f[4] += c.x; f[5] += c.y; f[6] += d.x; f[7] += d.y;
+        }
+      }
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        // pair mode: unit 0 / 1 of a row hold pixel 2x / 2x+1, each with its own channels 0..2
+        const bool resid_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
+        if ((flags & EPI_RESID_IN) && j == 0 && resid_unit && valid) {
+          // temp1 residual (bsvd_arch.py:394, 408-414): out[:, :3] = in[:, :3] - out[:, :3]
+          if (use_rin) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) f[i] = rin[i] - f[i];
+          } else {
+            const int xr = p.pair_px ? 2 * x + (nbase >> 5) : x;
+            const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : (p.pair_px ? 2 * p.W : p.W);
+            const long long plane = static_cast<long long>(sH) * sW;
+            const float* r = p.resid_in + (static_cast<long long>(tc.t) * p.resid_C) * plane +
+                             static_cast<long long>(reflect_src(y, sH)) * sW + reflect_src(xr, sW);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) f[i] = __ldg(r + i * plane) - f[i];
+          }
+        }
+      }
+      if constexpr (kSplit) {
+        // fp32-grade mode: the activation is applied in fp32, then the value leaves as hi + lo
+        if (flags & EPI_RELU6) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = relu6f(f[i]);
+        } else if (flags & EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+      }
+      if constexpr (!BF16) {
+        if (chk_range) {
+          if (chk_signed) {
+            vmax = fmaxf(fmaxf(vmax, f[0]), fmaxf(f[1], f[2]));
+            vmax = fmaxf(fmaxf(vmax, f[3]), fmaxf(f[4], f[5]));
+            vmax = fmaxf(vmax, fmaxf(f[6], f[7]));
+          } else {
+            vmax = fmaxf(fmaxf(vmax, fabsf(f[0])), fmaxf(fabsf(f[1]), fabsf(f[2])));
+            vmax = fmaxf(fmaxf(vmax, fabsf(f[3])), fmaxf(fabsf(f[4]), fabsf(f[5])));
+            vmax = fmaxf(vmax, fmaxf(fabsf(f[6]), fabsf(f[7])));
+          }
+        }
+      }
+      o[j].x = pack2<BF16>(f[0], f[1]); o[j].y = pack2<BF16>(f[2], f[3]);
+      o[j].z = pack2<BF16>(f[4], f[5]); o[j].w = pack2<BF16>(f[6], f[7]);
+      if constexpr (kSplit) {
+        const float2 h0 = unpack2<false>(o[j].x), h1 = unpack2<false>(o[j].y),
+                     h2 = unpack2<false>(o[j].z), h3 = unpack2<false>(o[j].w);
+        olo[j].x = pack2<false>(f[0] - h0.x, f[1] - h0.y); olo[j].y = pack2<false>(f[2] - h1.x, f[3] - h1.y);
+        olo[j].z = pack2<false>(f[4] - h2.x, f[5] - h2.y); olo[j].w = pack2<false>(f[6] - h3.x, f[7] - h3.y);
+      }
+      if constexpr ((MASK & EPI_RESID_IN) != 0) {
+        const bool aux_unit = p.pair_px ? ((nbase & 31) == 0) : (nbase == 0);
+        if ((flags & EPI_RESID_IN) && j == 0 && aux_unit && valid && p.aux_out) {
+          const long long pix = p.pair_px
+              ? (static_cast<long long>(tc.t) * p.H + y) * (2 * p.W) + 2 * x + (nbase >> 5)
+              : (static_cast<long long>(tc.t) * p.H + y) * p.W + x;
+          if constexpr (kSplit) reinterpret_cast<float4*>(p.aux_out)[pix] = make_float4(f[0], f[1], f[2], f[3]);
+          else reinterpret_cast<uint2*>(p.aux_out)[pix] = make_uint2(o[j].x, o[j].y);
+        }
+      }
+      if constexpr (!kSplit) {
+        if (flags & EPI_RELU6) {
+          o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
+          o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
+        } else if (flags & EPI_RELU) {
+          o[j].x = relu_packed<BF16>(o[j].x); o[j].y = relu_packed<BF16>(o[j].y);
+          o[j].z = relu_packed<BF16>(o[j].z); o[j].w = relu_packed<BF16>(o[j].w);
+        }
+      }
+    }
+    if constexpr (!BF16) {
+      // fp16 range guard (see ConvParams::overflow): a value that rounds to inf (|x| >= 65520).  A NaN can
+      // only come from an inf stored by an earlier stage, which raised the (sticky) flag there.
+      if (chk_range && __any_sync(0xffffffffu, valid && !(vmax < 65520.f)) && lane == 0) atomicOr(p.overflow, 1u);
+    }
+  }
+  if constexpr (kSplit) {
+    // two staging tiles per warp: hi through the first, lo through the second
+    epilogue_emit<BF16, MASK>(p, tc, el, y, nbase, o, stg, quad, lane, 0, map_o);
+    epilogue_emit<BF16, MASK>(p, tc, el, y, nbase, olo, stg + kStageBytesPerWarp, quad, lane, p.out_C, map_o);
+  } else {
+    epilogue_emit<BF16, MASK>(p, tc, el, y, nbase, o, stg, quad, lane, 0, map_o);
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -927,13 +980,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // re-materialises them from the constant bank with uniform loads, which is the faster of the two.
   struct {
     int a_stages, w_stages, cin_chunks, tap_begin, tap_end, mode, w_resident, total_tiles, desc_variant,
-        skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0;
+        skip_mma, w_rows_cta, cin_total, out_C_log2, out_C, skip_t0, phys_chunks, out_pitch_C, skip_blocks;
     uint32_t a_stage_bytes, w_stage_bytes, a_tx_bytes;
   } const pp = {p.a_stages, p.w_stages, p.cin_chunks, PIPE == 3 ? p.tap_begin : 0,
                 PIPE == 3 ? p.tap_end : (PIPE == 2 ? 3 : PIPE == 5 ? 6 : 9),
                 PIPE == 3 ? p.mode : PIPE, PIPE == 3 ? p.w_resident : (PIPE == 2 ? 1 : 0),
                 p.total_tiles, p.desc_variant, p.skip_mma, p.w_rows_cta, p.cin_total, p.out_C_log2, p.out_C,
-                p.skip_t0, p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
+                p.skip_t0, p.phys_chunks > 0 ? p.phys_chunks : p.cin_chunks, p.out_pitch_C,
+                p.skip_blocks > 0 ? p.skip_blocks : (p.skip_mma > 0 ? p.skip_mma : 1),
+                p.a_stage_bytes, p.w_stage_bytes, p.a_tx_bytes};
   const int ntaps = pp.tap_end - pp.tap_begin;
   // bytes one stage receives in total (both CTAs of a pair signal the leader's barrier)
   const uint32_t a_tx = CTA2 ? 2 * pp.a_tx_bytes : pp.a_tx_bytes;
@@ -959,7 +1014,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_wait(a_empty(sa), pa ^ 1);
                 if (rank == 0) mbar_expect_tx(a_full(sa), 2 * bytes);
                 tma_load_5d_2sm(a_base + sa * pp.a_stage_bytes, py ? &map_a : &map_s, a_full(sa),
-                                px * pp.cin_total + c * kChunk, (px || PIPE == 5) ? tc.x0 - 1 : tc.x0, py,
+                                px * pp.cin_total + (c % pp.phys_chunks) * kChunk, (px || PIPE == 5) ? tc.x0 - 1 : tc.x0, py,
                                 py ? tc.y0 - 1 : tc.y0, tc.t);
                 if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
               }
@@ -978,10 +1033,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_wait(a_empty(sa), pa ^ 1);
             if (rank == 0) mbar_expect_tx(a_full(sa), a_tx);
             if constexpr (CTA2)
-              tma_load_4d_2sm(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), c * kChunk,
+              tma_load_4d_2sm(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), (c % pp.phys_chunks) * kChunk,
                               tc.x0 - 1, tc.y0 - 1, tc.t);
             else
-              tma_load_4d(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), c * kChunk, tc.x0 - 1,
+              tma_load_4d(a_base + sa * pp.a_stage_bytes, &map_a, a_full(sa), (c % pp.phys_chunks) * kChunk, tc.x0 - 1,
                           tc.y0 - 1, tc.t);
             if (++sa == (uint32_t)pp.a_stages) { sa = 0; pa ^= 1; }
           }
@@ -1025,9 +1080,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (nskip < pp.skip_mma && (((c * ntaps + tap - pp.tap_begin) + 1) & 3) == 0) {
                 mbar_wait(w_empty(sw), pw ^ 1);
                 if (rank == 0) mbar_expect_tx(w_full(sw), w_tx);
-                const int n = tc.nt * NTILE + nskip * 64;
+                // split mode: blocks [0, skip_blocks) are the hi halves, the next skip_blocks the lo halves
+                const int n = tc.nt * NTILE + (nskip % pp.skip_blocks) * 64;
                 const int q = n >> pp.out_C_log2, ch = n & (pp.out_C - 1);
-                tma_load_4d_2sm(w_base + sw * pp.w_stage_bytes, &map_s, w_full(sw), (q & 1) * pp.out_C + ch,
+                tma_load_4d_2sm(w_base + sw * pp.w_stage_bytes, &map_s, w_full(sw),
+                                (q & 1) * pp.out_pitch_C + ch + (nskip >= pp.skip_blocks ? pp.out_C : 0),
                                 tc.x0, 2 * tc.y0 + (q >> 1), tc.t + pp.skip_t0);
                 ++nskip;
                 if (++sw == (uint32_t)pp.w_stages) { sw = 0; pw ^= 1; }
@@ -1213,7 +1270,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (leader && !dbg_no_mma) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16_2sm(tmem_acc + nskip * 64, desc_hi | (s_lo0 + k * 2u), desc_hi | (id_lo0 + k * 2u),
+                    umma_f16_2sm(tmem_acc + (nskip % pp.skip_blocks) * 64, desc_hi | (s_lo0 + k * 2u), desc_hi | (id_lo0 + k * 2u),
                                  make_idesc(64, BF16 ? 1 : 0, 256), 1u);
                 }
                 if (leader) umma_commit_2sm(w_empty(sw));
@@ -1245,7 +1302,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t stg0 = stg_base + ew * p.stg_bytes_per_warp;
     uint32_t ucount = 0;                       // TMA stores: units alternate between two staging tiles
     auto next_stg = [&]() -> uint32_t {
-      if constexpr ((MASK & EPI_TMA_OUT) != 0)
+      if constexpr ((MASK & EPI_SPLIT) != 0) return stg0;      // a unit uses both tiles itself (hi, lo)
+      else if constexpr ((MASK & EPI_TMA_OUT) != 0)
         return stg0 + ((p.stg_bytes_per_warp > kStageBytesPerWarp) ? (ucount++ & 1u) * kStageBytesPerWarp : 0u);
       else return stg0;
     };

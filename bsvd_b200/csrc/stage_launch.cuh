@@ -33,6 +33,8 @@ struct StageLaunch {
   size_t smem = 0;
   int ntile = 0, rows = 0;
   int cta2 = 0;         // 1 = cta_group::2 kernel, launched as clusters of 2 CTAs
+  int split = 0;        // 1 = fp32-grade mode (EPI_SPLIT instances, fp16 pieces)
+  const void* in_ptr = nullptr;   // fp32-grade edge convs (split_edge.cuh): the stage's input tensor
   int ew = 8;           // epilogue warps (8 or 16)
   // fused first stage (first_conv.cuh): raw network input, patched per call
   const float* first_in = nullptr;
@@ -64,7 +66,7 @@ static int launch_inst(const StageLaunch& L, cudaStream_t st) {
     }
     if (L.p.desc_variant != 0 || L.p.tap_begin != 0 || L.p.tap_end != (mode == 2 ? 3 : 9)) {
       // debug switches / partial tap ranges only exist in the generic pipeline
-    } else if constexpr (NTILE == 64 && R == 2) {
+    } else if constexpr (NTILE == 64 && R == 2 && (MASK & EPI_SPLIT) == 0) {
       if (mode == 2 && res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 2>(L, st);
     } else {
       if (mode == 0 && !res) return launch_pipe<NTILE, R, BF16, CTA2, MASK, EW, 0>(L, st);
@@ -117,6 +119,25 @@ constexpr int kMaskUpSkip = EPI_PIXSHUF | EPI_SKIP;                    // c32 up
 constexpr int kMaskAll = kMaskAct | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
+  if (L.split) {
+    // fp32-grade mode: every stored value leaves as a (hi, lo) fp16 pair (EPI_SPLIT); the skip add always
+    // runs on the tensor core, so the instance set is small
+    if constexpr (!BF16) {
+      const int f = L.p.flags & kMaskAll;
+      if (!L.cta2) return fail("the fp32-grade mode needs the CTA-pair kernels");
+      if (L.p.tma_out) {
+        if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, false, true, kMaskPlain | EPI_TMA_OUT | EPI_SPLIT, 8>(L, st);
+        if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, false, true, kMaskResid | EPI_TMA_OUT | EPI_SPLIT, 8>(L, st);
+        if constexpr (NTILE == 256 && R == 1)
+          if ((f & ~kMaskUpTma) == 0) return launch_inst<NTILE, R, false, true, kMaskUpTma | EPI_SPLIT, 8>(L, st);
+      }
+      if constexpr (NTILE != 64)
+        if ((f & ~kMaskShift) == 0) return launch_inst<NTILE, R, false, true, kMaskShift | EPI_SPLIT, 8>(L, st);
+      if constexpr (NTILE == 256 && R == 1)
+        if ((f & ~kMaskUpShift) == 0) return launch_inst<NTILE, R, false, true, kMaskUpShift | EPI_SPLIT, 8>(L, st);
+    }
+    return fail("no fp32-grade kernel instance for this stage (NTILE=%d R=%d flags=%d)", NTILE, R, L.p.flags);
+  }
   if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
   const int f = L.p.flags & kMaskAll;
   {

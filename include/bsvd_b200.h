@@ -32,7 +32,16 @@ typedef struct bsvd_handle bsvd_handle;
 
 /* Operand precision of the tensor-core contractions (accumulation is always fp32,
  * bias/activation/residual arithmetic is fp32, activations are stored in this type). */
-enum { BSVD_PREC_FP16 = 0, BSVD_PREC_BF16 = 1 };
+enum {
+  BSVD_PREC_FP16 = 0,
+  BSVD_PREC_BF16 = 1,
+  /* fp32-grade: for callers that run the reference with val.fp16 False and TF32 off
+   * (Experimental_root/models/denoising_model.py:204).  Every activation and weight is carried as a pair of
+   * fp16 numbers (x = hi + lo) and every contraction is three tensor-core products
+   * (W_hi x_hi + W_hi x_lo + W_lo x_hi, fp32 accumulation), the first / last conv run in fp32 on the CUDA
+   * cores: ~1e-5 from the fp32 reference at about a third of the fp16 mode's speed.  BSVD-64 only. */
+  BSVD_PREC_FP32X3 = 2
+};
 
 /* Mirrors the constructor kwargs of BSVD (bsvd_arch.py:446-447) as passed by
  * options/test/bsvd_c64.yml:85-93: chns={64,128,256}, mid_ch=64, interm_ch=64, in_ch=4 (3 = blind),

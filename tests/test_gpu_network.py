@@ -728,3 +728,61 @@ def test_denoise_folder_reads_pngs_writes_pngs_and_reports_metrics(tmp_path):
     with torch.no_grad():
         direct = net.denoise_frames_u8(fr, 20.0 / 255.0, bgr=True)
     assert out2["psnr"] is None and np.array_equal(out2["result_u8"], direct.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: fp32-grade mode (precision='fp32x3': hi/lo fp16 pairs, three tensor-core products per contraction)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_fp32x3_mode_matches_reference_fixture_at_fp32_grade(path):
+    """For callers that run the reference with val.fp16 False / TF32 off (denoising_model.py:204): the
+    trained-like fixtures to 1e-4, and the saturating default-init fixture — where the 16-bit modes are only
+    checked relatively — to 1e-3 * max(1, |y|max / 4)."""
+    g = np.load(path)
+    net, _ = make_net(int(g["param_seed"]), float(g["weight_scale"]), "fp32x3")
+    x, _ = O.make_synthetic_clip(int(g["T"]), int(g["H"]), int(g["W"]), int(g["clip_seed"]))
+    with torch.no_grad():
+        y = net(x[None, :, :3].cuda(), noise_map=x[None, :, 3:4].cuda())[0].float().cpu()
+    ref = torch.from_numpy(g["y_stream"])
+    err = float((y - ref).abs().max())
+    if float(g["weight_scale"]) < 1.0:
+        assert err <= 1e-4, err
+    else:
+        assert err <= 1e-3 * max(1.0, float(ref.abs().max()) / 4), (err, float(ref.abs().max()))
+    assert net.last_launch_count == 32
+
+
+def test_fp32x3_mode_sizes_stream_and_fused_entry():
+    net, layers = make_net(prec="fp32x3")
+    for (T, H, W) in ((3, 36, 260), (2, 136, 264), (10, 4, 4)):
+        x, _ = O.make_synthetic_clip(T, H, W, seed=91)
+        with torch.no_grad():
+            y = net(x[None].cuda())[0].float().cpu()
+        ref = O.forward_clip(layers, x)
+        assert float((y - ref).abs().max()) <= 1e-4, (T, H, W)
+    # streaming schedule (rings with hi|lo pitch, graph replays) bit-identical to the clip schedule
+    xs, _ = O.make_synthetic_clip(22, 24, 40, seed=92)
+    with torch.no_grad():
+        yc = net(xs[None].cuda())[0]
+        net.reset()
+        outs, _ = _drive_stream(net, xs)
+        net.reset()
+    assert torch.equal(torch.cat([o for o in outs if o is not None]), yc)
+    # fused pad / sigma / clamp / crop entry on an odd size == the unfused steps
+    from bsvd_b200 import pipeline
+    xo, _ = O.make_synthetic_clip(2, 30, 45, seed=93)
+    noisy = xo[:, :3].clamp(0, 1).contiguous().cuda()
+    with torch.no_grad():
+        a = net.denoise_sequence(noisy, 20.0 / 255.0)
+        b = pipeline.denoise_sequence_unfused(net, noisy, 20.0 / 255.0)
+    assert torch.equal(a, b)
+    assert not net.overflowed()
+
+
+def test_fp32x3_full_size_against_oracle():
+    net, layers = make_net(prec="fp32x3")
+    x, _ = O.make_synthetic_clip(2, 540, 960, seed=1)
+    with torch.no_grad():
+        y = net(x[None].cuda())[0].float().cpu()
+    ref = O.forward_clip(layers, x)
+    assert float((y - ref).abs().max()) <= 1e-4
