@@ -13,6 +13,11 @@ for the step to finish or, once resident, makes the stage kernels run in two wav
     g = gather.wait(step)                            # current stream waits; returns the [world, *shape] view
 
 The reference's counterpart is DataParallel's scatter/gather (BasicSR/basicsr/models/base_model.py:74-75).
+
+`PeerGroup(..., backend="shm")` is the same interface over POSIX shared memory between CPU processes
+(numpy memmaps under /dev/shm, flags polled by the waiting process): it exists so that the host-side
+protocols — ring slots, ready / free flags, strip geometry — run under world_size-2 gloo tests on a box
+without GPUs (tests/test_tiling.py).  It is test infrastructure, never a fallback of the GPU path.
 """
 from __future__ import annotations
 
@@ -23,18 +28,40 @@ import torch
 from . import capi
 
 
-class PeerGroup:
-    """A symmetric device buffer (data + flags) on every rank, mapped into every other rank."""
+class _NoStream:
+    """Stands for streams / events in the shared-memory backend (everything is program order there)."""
+    cuda_stream = 0
 
-    def __init__(self, nbytes: int, nflags: int, group=None):
+    def wait_event(self, ev):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class PeerGroup:
+    """A symmetric buffer (data + flags) on every rank, mapped into every other rank.
+    backend "cuda": device memory shared through CUDA IPC, copy-engine transfers (the product path);
+    backend "shm" : host shared memory between CPU processes (protocol tests only)."""
+
+    def __init__(self, nbytes: int, nflags: int, group=None, backend: str = "cuda"):
         import torch.distributed as dist
-        self.lib = capi.load_library()
         self.dist_group = group
+        self.backend = backend
         if dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:
             self.rank, self.world = 0, 1
         self.nbytes, self.nflags = int(nbytes), int(nflags)
+        if backend == "shm":
+            self._init_shm(group)
+            return
+        if backend != "cuda":
+            raise ValueError("backend must be 'cuda' or 'shm'")
+        self.lib = capi.load_library()
         self.device = torch.device("cuda", torch.cuda.current_device())
         h = C.c_void_p()
         capi.check(self.lib.bsvd_peer_create(self.rank, self.world, self.nbytes, self.nflags, C.byref(h)))
@@ -52,6 +79,36 @@ class PeerGroup:
         self.data_ptr = int(self.lib.bsvd_peer_local_data(self._h))
         self.side = torch.cuda.Stream(device=self.device)      # transfers are enqueued here
 
+    # ---- shared-memory backend (CPU processes; tests) ---------------------------------------------
+    def _init_shm(self, group):
+        import os
+        import uuid
+        import numpy as np
+        import torch.distributed as dist
+        self.device = torch.device("cpu")
+        self.side = _NoStream()
+        self._flag_bytes = (self.nflags * 4 + 4095) // 4096 * 4096
+        name = f"/dev/shm/bsvd_peer_{os.getpid()}_{uuid.uuid4().hex[:8]}_{self.rank}"
+        mm = np.memmap(name, dtype=np.uint8, mode="w+", shape=(self._flag_bytes + self.nbytes,))
+        mm[:] = 0
+        mm.flush()
+        names = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(names, name, group=group)
+        else:
+            names = [name]
+        self._names = names
+        self._maps = [mm if r == self.rank else np.memmap(names[r], dtype=np.uint8, mode="r+",
+                                                           shape=(self._flag_bytes + self.nbytes,))
+                      for r in range(self.world)]
+        self._flags = [m[:self.nflags * 4].view(np.uint32) for m in self._maps]
+        self._h = "shm"
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def _shm_data(self, r):
+        return self._maps[r][self._flag_bytes:]
+
     # ---- views ---------------------------------------------------------------------------------
     def local_tensor(self, offset: int, shape, dtype=torch.float32) -> torch.Tensor:
         """A torch view of the local data area (no copy; lives as long as the group)."""
@@ -61,7 +118,11 @@ class PeerGroup:
         esz = torch.empty((), dtype=dtype).element_size()
         if offset < 0 or offset + n * esz > self.nbytes:
             raise ValueError("view outside the peer buffer")
-        arr = (C.c_ubyte * (n * esz)).from_address(self.data_ptr + offset)
+        if self.backend == "shm":
+            import numpy as np
+            npdt = {torch.float32: np.float32, torch.float16: np.float16, torch.uint8: np.uint8, torch.int32: np.int32}[dtype]
+            arr = self._shm_data(self.rank)[offset:offset + n * esz].view(npdt).reshape(tuple(int(s) for s in shape))
+            return torch.from_numpy(arr)
 
         class _Holder:        # __cuda_array_interface__ provider
             pass
@@ -69,12 +130,17 @@ class PeerGroup:
         typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
         hold.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
                                          "data": (self.data_ptr + offset, False), "version": 2}
-        hold._keep = (self, arr)
+        hold._keep = self
         return torch.as_tensor(hold, device=self.device)
 
     # ---- one-sided operations ------------------------------------------------------------------
     def put(self, dst_rank: int, dst_off: int, src: torch.Tensor, stream=None):
-        assert src.is_cuda and src.is_contiguous()
+        assert src.is_contiguous()
+        if self.backend == "shm":
+            b = src.numpy().reshape(-1).view("uint8")
+            self._shm_data(dst_rank)[dst_off:dst_off + b.size] = b
+            return
+        assert src.is_cuda
         st = (stream or self.side).cuda_stream
         capi.check(self.lib.bsvd_peer_put(self._h, dst_rank, dst_off, src.data_ptr(),
                                           src.numel() * src.element_size(), st))
@@ -85,33 +151,79 @@ class PeerGroup:
         capi.check(self.lib.bsvd_peer_put2d(self._h, dst_rank, dst_off, dst_pitch, src_ptr, src_pitch,
                                             width_bytes, rows, st))
 
-    def put3d(self, dst_rank: int, dst_off: int, dst_pitch: int, dst_plane_rows: int, src_ptr: int,
-              src_pitch: int, src_plane_rows: int, width_bytes: int, rows: int, planes: int, stream=None):
+    def put3d(self, dst_rank: int, dst_off: int, dst_pitch: int, dst_plane_rows: int, src,
+              src_pitch: int, src_plane_rows: int, width_bytes: int, rows: int, planes: int, stream=None,
+              src_off: int = 0):
+        """planes x rows x width_bytes block.  `src` is a device pointer (int), or a tensor whose storage
+        the block is cut from starting `src_off` bytes in."""
+        if self.backend == "shm":
+            import numpy as np
+            sb = src.numpy().reshape(-1).view(np.uint8)
+            dd = self._shm_data(dst_rank)
+            for pl in range(planes):
+                for r in range(rows):
+                    so = src_off + (pl * src_plane_rows + r) * src_pitch
+                    do = dst_off + (pl * dst_plane_rows + r) * dst_pitch
+                    dd[do:do + width_bytes] = sb[so:so + width_bytes]
+            return
+        src_ptr = (src.data_ptr() + src_off) if torch.is_tensor(src) else int(src) + src_off
         st = (stream or self.side).cuda_stream
         capi.check(self.lib.bsvd_peer_put3d(self._h, dst_rank, dst_off, dst_pitch, dst_plane_rows, src_ptr,
                                             src_pitch, src_plane_rows, width_bytes, rows, planes, st))
 
     def signal(self, dst_rank: int, flag: int, value: int, stream=None):
+        if self.backend == "shm":
+            self._flags[dst_rank][flag] = value
+            return
         st = (stream or self.side).cuda_stream
         capi.check(self.lib.bsvd_peer_signal(self._h, dst_rank, flag, value, st))
 
-    def wait(self, flag: int, value: int, stream=None):
+    def wait(self, flag: int, value: int, stream=None, timeout_s: float = 120.0):
+        if self.backend == "shm":
+            import time
+            t0 = time.time()
+            while int(self._flags[self.rank][flag]) < value:
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"rank {self.rank}: flag {flag} never reached {value}")
+                time.sleep(0.0005)
+            return
         st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
         capi.check(self.lib.bsvd_peer_wait(self._h, flag, value, st))
 
     def read_flag(self, flag: int) -> int:
+        if self.backend == "shm":
+            return int(self._flags[self.rank][flag])
         v = C.c_uint(0)
         capi.check(self.lib.bsvd_peer_read_flag(self._h, flag, C.byref(v)))
         return int(v.value)
 
+    def current_stream(self):
+        return _NoStream() if self.backend == "shm" else torch.cuda.current_stream(self.device)
+
+    def new_event(self):
+        return _NoStream() if self.backend == "shm" else torch.cuda.Event()
+
     def close(self):
-        if getattr(self, "_h", None) is not None:
-            torch.cuda.synchronize(self.device)
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.barrier(group=self.dist_group)     # peers may still be writing into / reading from us
+        if getattr(self, "_h", None) is None:
+            return
+        if self.world > 1:
+            import torch.distributed as dist
+            if self.backend == "cuda":
+                torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.dist_group)     # peers may still be writing into / reading from us
+        if self.backend == "shm":
+            import os
+            self._flags = None
+            self._maps = None
+            try:
+                os.unlink(self._names[self.rank])
+            except OSError:
+                pass
+        else:
+            if self.world == 1:
+                torch.cuda.synchronize(self.device)
             self.lib.bsvd_peer_destroy(self._h)
-            self._h = None
+        self._h = None
 
 
 def gather_layout(world: int, slot_bytes: int, depth: int = 2):
@@ -137,7 +249,7 @@ class ClipGather:
     release(step): the calling stream's reads of the slot are done — tell the producers.
     """
 
-    def __init__(self, shape, dtype=torch.float32, depth: int = 2, group=None):
+    def __init__(self, shape, dtype=torch.float32, depth: int = 2, group=None, backend: str = "cuda"):
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.shape, self.dtype, self.depth = tuple(int(s) for s in shape), dtype, depth
@@ -146,17 +258,17 @@ class ClipGather:
             n *= s
         self.slot_bytes = n * torch.empty((), dtype=dtype).element_size()
         self.lay = gather_layout(world, self.slot_bytes, depth)
-        self.pg = PeerGroup(self.lay["bytes"], self.lay["nflags"], group)
+        self.pg = PeerGroup(self.lay["bytes"], self.lay["nflags"], group, backend=backend)
         self.world, self.rank = self.pg.world, self.pg.rank
-        self.ev = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_rel = torch.cuda.Event()
-        self.ev_put = [torch.cuda.Event() for _ in range(depth)]
+        self.ev = [self.pg.new_event() for _ in range(depth)]
+        self.ev_rel = self.pg.new_event()
+        self.ev_put = [self.pg.new_event() for _ in range(depth)]
 
     def put(self, y: torch.Tensor, step: int):
         assert tuple(y.shape) == self.shape and y.dtype == self.dtype and y.is_contiguous()
         pg, k = self.pg, step % self.depth
         ev = self.ev[k]
-        ev.record(torch.cuda.current_stream(pg.device))
+        ev.record(pg.current_stream())
         pg.side.wait_event(ev)
         if step >= self.depth:
             for r in range(self.world):              # slot k was last used by step - depth
@@ -165,7 +277,8 @@ class ClipGather:
             r = (self.rank + 1 + i) % self.world
             pg.put(r, self.lay["data"](k, self.rank), y, stream=pg.side)
             pg.signal(r, self.lay["ready"](k, self.rank), step + 1, stream=pg.side)
-        y.record_stream(pg.side)
+        if y.is_cuda:
+            y.record_stream(pg.side)
         done = self.ev_put[k]
         done.record(pg.side)          # y has been read: its owner may overwrite it after this event
         return done
@@ -179,7 +292,7 @@ class ClipGather:
     def release(self, step: int):
         """Reads of slot `step` enqueued on the current stream so far are the last ones."""
         pg, k = self.pg, step % self.depth
-        self.ev_rel.record(torch.cuda.current_stream(pg.device))
+        self.ev_rel.record(pg.current_stream())
         pg.side.wait_event(self.ev_rel)
         for r in range(self.world):
             pg.signal(r, self.lay["free"](k, self.rank), step + 1, stream=pg.side)

@@ -161,7 +161,8 @@ class TileExchange:
       out_free [k]        on all  : the owner has consumed full-frame slot k
     """
 
-    def __init__(self, T, C, H, W, rows, cols, halo: int = HALO, owner: int = 0, depth: int = 2, group=None):
+    def __init__(self, T, C, H, W, rows, cols, halo: int = HALO, owner: int = 0, depth: int = 2, group=None,
+                 backend: str = "cuda"):
         from .peer import PeerGroup
         import torch.distributed as dist
         self.T, self.C, self.H, self.W, self.depth, self.owner = T, C, H, W, depth, owner
@@ -182,12 +183,12 @@ class TileExchange:
         self.f_in_free = lambda k, dst: depth * w + k * w + dst
         self.f_out_ready = lambda k, src: 2 * depth * w + k * w + src
         self.f_out_free = lambda k: 3 * depth * w + k
-        self.pg = PeerGroup(nbytes, 3 * depth * w + depth, group)
+        self.pg = PeerGroup(nbytes, 3 * depth * w + depth, group, backend=backend)
         self.rank, self.world = self.pg.rank, world
         self.me = self.tiles[self.rank]
-        self.ev_in = torch.cuda.Event()
-        self.ev_fwd = torch.cuda.Event()
-        self.ev_own = torch.cuda.Event()
+        self.ev_in = self.pg.new_event()
+        self.ev_fwd = self.pg.new_event()
+        self.ev_own = self.pg.new_event()
         me = self.me
         self.ring_bytes = T * C * 4 * ((me.hy1 - me.hy0) * (me.hx1 - me.hx0) - (me.y1 - me.y0) * (me.x1 - me.x0))
         self.received_bytes = 0
@@ -199,7 +200,7 @@ class TileExchange:
         pg, k, me, T, C = self.pg, step % self.depth, self.me, self.T, self.C
         th, tw = me.y1 - me.y0, me.x1 - me.x0
         assert tuple(x_tile.shape) == (T, C, th, tw) and x_tile.is_contiguous() and x_tile.dtype == torch.float32
-        cur = torch.cuda.current_stream(pg.device)
+        cur = pg.current_stream()
         self.ev_in.record(cur)
         pg.side.wait_event(self.ev_in)
         for dst, ya, yb, xa, xb in self.sends[self.rank]:
@@ -207,11 +208,13 @@ class TileExchange:
             dh, dw = d.hy1 - d.hy0, d.hx1 - d.hx0
             if step >= self.depth:
                 pg.wait(self.f_in_free(k, dst), step - self.depth + 1, stream=pg.side)
-            src_ptr = x_tile.data_ptr() + ((ya - me.y0) * tw + (xa - me.x0)) * 4
+            src_off = ((ya - me.y0) * tw + (xa - me.x0)) * 4
             dst_off = self.off_region(k) + ((ya - d.hy0) * dw + (xa - d.hx0)) * 4
-            pg.put3d(dst, dst_off, dw * 4, dh, src_ptr, tw * 4, th, (xb - xa) * 4, yb - ya, T * C, stream=pg.side)
+            pg.put3d(dst, dst_off, dw * 4, dh, x_tile, tw * 4, th, (xb - xa) * 4, yb - ya, T * C, stream=pg.side,
+                     src_off=src_off)
             pg.signal(dst, self.f_in_ready(k, self.rank), step + 1, stream=pg.side)
-        x_tile.record_stream(pg.side)
+        if x_tile.is_cuda:
+            x_tile.record_stream(pg.side)
         # ---- forward on the enlarged tile once every contributor's strip has landed
         for src in self.recv_from[self.rank]:
             pg.wait(self.f_in_ready(k, src), step + 1)
@@ -229,11 +232,13 @@ class TileExchange:
         if step >= self.depth:
             pg.wait(self.f_out_free(k), step - self.depth + 1, stream=pg.side)
         y = y.contiguous()
-        src_ptr = y.data_ptr() + ((me.y0 - me.hy0) * ww + (me.x0 - me.hx0)) * 4
+        src_off = ((me.y0 - me.hy0) * ww + (me.x0 - me.hx0)) * 4
         dst_off = self.off_full(k) + (me.y0 * self.W + me.x0) * 4
-        pg.put3d(self.owner, dst_off, self.W * 4, self.H, src_ptr, ww * 4, hh, tw * 4, th, T * 3, stream=pg.side)
+        pg.put3d(self.owner, dst_off, self.W * 4, self.H, y, ww * 4, hh, tw * 4, th, T * 3, stream=pg.side,
+                 src_off=src_off)
         pg.signal(self.owner, self.f_out_ready(k, self.rank), step + 1, stream=pg.side)
-        y.record_stream(pg.side)
+        if y.is_cuda:
+            y.record_stream(pg.side)
         if self.rank == self.owner:
             return pg.local_tensor(self.off_full(k), (T, 3, self.H, self.W))
         return None
@@ -247,7 +252,7 @@ class TileExchange:
     def release_full(self, step: int):
         """Owner: reads of the full frame of `step` enqueued on the current stream so far are the last."""
         pg, k = self.pg, step % self.depth
-        self.ev_own.record(torch.cuda.current_stream(pg.device))
+        self.ev_own.record(pg.current_stream())
         pg.side.wait_event(self.ev_own)
         for r in range(self.world):
             pg.signal(r, self.f_out_free(k), step + 1, stream=pg.side)

@@ -105,3 +105,82 @@ def test_exchange_plan_strips_rebuild_every_enlarged_region():
     tiles = tiling.tile_plan(2160, 3840, 2, 4)
     sends, _ = tiling.exchange_plan(tiles)
     assert max(len(s) for s in sends) <= 9 and all(len(s) < len(tiles) for s in sends)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the one-sided protocols of the multi-GPU path (bsvd_b200/peer.py ClipGather, tiling.TileExchange) under
+# world_size-2 gloo on the CPU: same host code as on the GPUs, PeerGroup(backend="shm") in place of the
+# CUDA-IPC buffers (ring slots, ready / free flags, strip geometry, slot reuse over more steps than slots)
+# ---------------------------------------------------------------------------------------------------
+def _peer_worker(rank, world, port, mode, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    ok = True
+    if mode == "gather":
+        from bsvd_b200.peer import ClipGather
+        shape = (2, 3, 12, 20)
+        g = ClipGather(shape, torch.float32, depth=2, backend="shm")
+        for i in range(7):                                  # 7 steps through 2 slots: free flags are exercised
+            torch.manual_seed(100 * i + rank)
+            y = torch.randn(shape)
+            want = [torch.empty(shape) for _ in range(world)]
+            dist.all_gather(want, y)
+            g.put(y, i)
+            got = g.wait(i).clone()
+            g.release(i)
+            ok = ok and torch.equal(got, torch.stack(want))
+        ok = ok and g.pg.read_flag(g.lay["ready"](0, 1 - rank)) == 7      # last even step 6 -> value 7
+        g.close()
+        q.put((rank, ok))
+    else:
+        fwd = _oracle_forward()
+        T, H, W = 1, 48, 328
+        ex = tiling.TileExchange(T, 4, H, W, 1, world, owner=0, backend="shm")
+        me = ex.me
+        outs = []
+        for i in range(3):                                  # 3 steps through 2 slots
+            x, _ = O.make_synthetic_clip(T, H, W, seed=6 + i)
+            full = ex.step(fwd, x[:, :, me.y0:me.y1, me.x0:me.x1].contiguous(), i)
+            if rank == 0:
+                ex.wait_full(i)
+                outs.append(full.clone().numpy())
+                ex.release_full(i)
+        info = (ex.received_bytes, ex.ring_bytes)
+        ex.close()
+        q.put((rank, outs if rank == 0 else None, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_peer_workers(mode):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(res, key=lambda r: r[0])
+
+
+def test_clip_gather_protocol_world2_gloo_shared_memory():
+    res = _run_peer_workers("gather")
+    assert all(r[1] for r in res), res
+
+
+def test_tile_exchange_protocol_world2_gloo_shared_memory():
+    res = _run_peer_workers("tiles")
+    outs, (recv, ring) = res[0][1], res[0][2]
+    assert recv == ring and res[1][2][0] == res[1][2][1]
+    fwd = _oracle_forward()
+    for i, got in enumerate(outs):
+        x, _ = O.make_synthetic_clip(1, 48, 328, seed=6 + i)
+        full = fwd(x)
+        assert float((torch.from_numpy(got) - full).abs().max()) < 2e-5
