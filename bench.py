@@ -705,11 +705,15 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-fp32x3", action="store_true")
+    ap.add_argument("--shape", default=None, help="T,H,W override for smoke tests of this script (NOT the benchmark config)")
     ap.add_argument("--sustained-steps", type=int, default=40)
     ap.add_argument("--quick-parity", action="store_true", help="parity on 2 frames instead of all 10")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the outputs are gathered (p2p = copy engines over NVLink, overlapped)")
     args = ap.parse_args()
+    if args.shape:
+        global T_CLIP, H, W
+        T_CLIP, H, W = (int(v) for v in args.shape.split(","))
     if args.impl == "reference":
         run_reference(args)
     elif args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -78,3 +78,24 @@ def test_real_registry_and_yml(tmp_path, monkeypatch):
     got = O.layers_from_bsvd_state(net.state_dict())
     want = O.layers_from_tsn_state(O.make_synthetic_params(0))
     assert all(torch.equal(a[0], b[0]) for a, b in zip(got, want))
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny shape: exactly one stdout line, the
+    contract's keys, and — when the unmodified reference is staged under baseline/_ref — kind 'reference'."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2",
+                        "--warmup", "1", "--shape", "3,16,24"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["steps"] == 2
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    staged = os.path.isdir(os.path.join(root, "baseline", "_ref", "Experimental_root"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
