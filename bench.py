@@ -306,11 +306,27 @@ def run_b200(args):
     # ---- multi-GPU: every rank's denoised clip is gathered on every rank.  Default: copy-engine puts
     # into peer-mapped rings over NVLink (bsvd_b200/peer.py), consumed on a side stream, so step i's
     # gather overlaps step i+1's compute and takes no SM.  --gather nccl: NCCL all_gather_into_tensor.
-    gather, gathered, consumer, chk = None, None, None, None
+    gather, gathered, consumer, chk, gather_note = None, None, None, None, None
     if world > 1:
+        gather_note = None
         if args.gather == "p2p":
+            # peer-mapped rings need CUDA IPC between the ranks' devices (one node, P2P access).  If any rank
+            # cannot set them up, ALL ranks fall back to the NCCL all_gather and the line says so.
             from bsvd_b200.peer import ClipGather
-            gather = ClipGather((T_CLIP, 3, H, W), torch.float32, depth=2)
+            err = ""
+            try:
+                gather = ClipGather((T_CLIP, 3, H, W), torch.float32, depth=2)
+            except Exception as e:  # noqa: BLE001
+                gather, err = None, f"{type(e).__name__}: {e}"
+            ok = torch.tensor([1 if gather is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if gather is not None:
+                    gather.close()
+                    gather = None
+                args.gather = "nccl"
+                gather_note = "peer-memory gather unavailable on this node (" + (err or "another rank failed") + "); NCCL all_gather used"
+        if args.gather == "p2p":
             consumer = torch.cuda.Stream(device=dev)
             chk = torch.zeros((), dtype=torch.float64, device=dev)
         else:
@@ -657,6 +673,7 @@ def run_b200(args):
                                    if args.gather == "p2p" else "NCCL all_gather_into_tensor on the compute stream"))
                    if world > 1 else "single GPU",
                    "gather": args.gather if world > 1 else None, "gather_matches_nccl": gather_check,
+                   "gather_note": gather_note if world > 1 else None,
                    "l2": "per-layer tensors are 0.17-0.66 GB each (working set 4.7 GB per step) >> 126 MB L2; no explicit flush needed",
                    "weights": "seeded synthetic, 0.5 x kaiming (SURVEY 8d); random init, no checkpoint available",
                    "profiling_during_timed_region": False},

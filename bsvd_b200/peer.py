@@ -63,19 +63,41 @@ class PeerGroup:
             raise ValueError("backend must be 'cuda' or 'shm'")
         self.lib = capi.load_library()
         self.device = torch.device("cuda", torch.cuda.current_device())
+        # Every rank goes through the same collectives whatever happens locally (a rank that raised early
+        # would leave the others in a mismatched collective): failures are recorded, agreed on with one
+        # all_reduce, and then raised on ALL ranks.
         h = C.c_void_p()
-        capi.check(self.lib.bsvd_peer_create(self.rank, self.world, self.nbytes, self.nflags, C.byref(h)))
+        err = None
+        if self.lib.bsvd_peer_create(self.rank, self.world, self.nbytes, self.nflags, C.byref(h)) != 0:
+            err = self.lib.bsvd_last_error().decode("utf-8", "replace")
+            h = None
         self._h = h
+        import os
+        if err is None and os.environ.get("BSVD_B200_PEER_FAIL") == str(self.rank):
+            err = "forced failure (BSVD_B200_PEER_FAIL, tests of the fallback)"
         if self.world > 1:
             hb = self.lib.bsvd_peer_handle_bytes()
             mine = (C.c_ubyte * hb)()
-            capi.check(self.lib.bsvd_peer_get_handle(self._h, mine))
+            if err is None and self.lib.bsvd_peer_get_handle(self._h, mine) != 0:
+                err = self.lib.bsvd_last_error().decode("utf-8", "replace")
             t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
             allh = torch.empty((self.world, hb), dtype=torch.uint8, device=self.device)
             dist.all_gather_into_tensor(allh, t, group=group)
-            buf = (C.c_ubyte * (hb * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
-            capi.check(self.lib.bsvd_peer_open(self._h, buf))
-            dist.barrier(group=group)          # nobody puts before everybody has mapped
+            okt = torch.tensor([0 if err else 1], device=self.device)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN, group=group)
+            if int(okt.item()) == 1:
+                buf = (C.c_ubyte * (hb * self.world)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+                if self.lib.bsvd_peer_open(self._h, buf) != 0:
+                    err = self.lib.bsvd_last_error().decode("utf-8", "replace")
+                okt = torch.tensor([0 if err else 1], device=self.device)
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN, group=group)   # also: nobody puts before everybody has mapped
+            if int(okt.item()) == 0:
+                if self._h is not None:
+                    self.lib.bsvd_peer_destroy(self._h)
+                    self._h = None
+                raise capi.BsvdError("peer memory could not be set up on every rank: " + (err or "another rank failed"))
+        elif err:
+            raise capi.BsvdError(err)
         self.data_ptr = int(self.lib.bsvd_peer_local_data(self._h))
         self.side = torch.cuda.Stream(device=self.device)      # transfers are enqueued here
 
