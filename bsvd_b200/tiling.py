@@ -40,8 +40,11 @@ class Tile:
     hx1: int          # enlarged region actually processed (clamped to the frame)
 
 
-def tile_plan(H: int, W: int, rows: int, cols: int, halo: int = HALO):
-    """rows x cols tiles whose edges are multiples of 4; row-major order (tile r*cols+c)."""
+def tile_plan(H: int, W: int, rows: int, cols: int, halo: int = HALO, balance: bool = False):
+    """rows x cols tiles whose edges are multiples of 4; row-major order (tile r*cols+c).
+    balance=True equalises the ENLARGED sizes instead of the owned ones: a tile in the middle carries the
+    halo on both sides, a tile at the frame border on one, so border tiles own `halo` more pixels and every
+    rank computes the same area (the slowest rank sets the step time)."""
     if H % 4 or W % 4:
         raise ValueError("H and W must be multiples of 4")
     if halo % 4:
@@ -50,6 +53,12 @@ def tile_plan(H: int, W: int, rows: int, cols: int, halo: int = HALO):
     def cuts(n, k):
         q = n // 4
         edges = [4 * ((q * i) // k) for i in range(k)] + [n]
+        if balance and k > 2:
+            e = (n + 2 * halo * (k - 1)) / k                      # common enlarged size
+            inner = max(4, int(round((e - 2 * halo) / 4)) * 4)    # owned by a tile with two halos
+            first = (n - inner * (k - 2)) // 2 // 4 * 4           # owned by the two border tiles (the last takes the rest)
+            if first >= 4 and n - first - inner * (k - 2) >= 4:
+                edges = [0] + [first + inner * i for i in range(k - 1)] + [n]
         if len(set(edges)) != len(edges):
             raise ValueError(f"cannot cut {n} pixels into {k} tiles of at least 4")
         return edges
@@ -162,11 +171,11 @@ class TileExchange:
     """
 
     def __init__(self, T, C, H, W, rows, cols, halo: int = HALO, owner: int = 0, depth: int = 2, group=None,
-                 backend: str = "cuda"):
+                 backend: str = "cuda", balance: bool = False):
         from .peer import PeerGroup
         import torch.distributed as dist
         self.T, self.C, self.H, self.W, self.depth, self.owner = T, C, H, W, depth, owner
-        self.tiles = tile_plan(H, W, rows, cols, halo)
+        self.tiles = tile_plan(H, W, rows, cols, halo, balance=balance)
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world != len(self.tiles):
             raise ValueError(f"{len(self.tiles)} tiles need {len(self.tiles)} ranks, got {world}")

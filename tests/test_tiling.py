@@ -24,6 +24,17 @@ def test_tile_plan_covers_frame_and_is_aligned():
         assert int(cover.min()) == 1 and int(cover.max()) == 1
     with pytest.raises(ValueError):
         tiling.tile_plan(18, 32, 1, 1)
+    # balanced plan: same coverage / alignment, equal ENLARGED sizes along an axis with more than two tiles
+    for (H, W, r, c) in [(2160, 3840, 4, 2), (2160, 3840, 2, 4), (540, 960, 1, 5)]:
+        tiles = tiling.tile_plan(H, W, r, c, balance=True)
+        cover = torch.zeros(H, W, dtype=torch.int32)
+        for t in tiles:
+            cover[t.y0:t.y1, t.x0:t.x1] += 1
+            assert all(v % 4 == 0 for v in (t.y0, t.y1, t.x0, t.x1, t.hy0, t.hy1, t.hx0, t.hx1))
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        areas = [(t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in tiles]
+        plain = [(t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in tiling.tile_plan(H, W, r, c)]
+        assert max(areas) < max(plain) and max(areas) - min(areas) <= 0.02 * max(areas)
 
 
 def _oracle_forward():

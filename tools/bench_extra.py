@@ -205,7 +205,7 @@ def tiles(args):
     dist.init_process_group("nccl", device_id=dev)
     net = make_net(args.precision, dev)
     T, H, W = args.frames, args.height, args.width
-    plan = tiling.tile_plan(H, W, args.rows, args.cols)
+    plan = tiling.tile_plan(H, W, args.rows, args.cols, balance=args.balance)
     t = plan[rank]
     # every rank synthesises the same frame and keeps only its own tile (stands for a decoder that
     # delivers tiles); the 80-px ring then comes from the neighbours
@@ -214,7 +214,7 @@ def tiles(args):
     fwd = lambda r: net(r[None])[0]  # noqa: E731
     ex, consumer, chk = None, None, None
     if args.exchange == "p2p":
-        ex = tiling.TileExchange(T, 4, H, W, args.rows, args.cols, owner=0)
+        ex = tiling.TileExchange(T, 4, H, W, args.rows, args.cols, owner=0, balance=args.balance)
         consumer = torch.cuda.Stream(device=dev)
         chk = torch.zeros((), dtype=torch.float64, device=dev)
     ev = torch.cuda.Event()
@@ -288,6 +288,8 @@ def tiles(args):
         if ex is not None:
             line["received_bytes_per_step"] = ex.received_bytes
             line["ring_bytes"] = ex.ring_bytes
+            line["balanced_tiles"] = bool(args.balance)
+            line["largest_enlarged_tile"] = max((q.hy1 - q.hy0) * (q.hx1 - q.hx0) for q in plan)
             line["redundant_compute"] = sum((q.hy1 - q.hy0) * (q.hx1 - q.hx0) for q in plan) / float(H * W)
         if single_ms is not None:
             line["single_gpu"] = {"ms_per_clip": single_ms, "value": T / (single_ms / 1e3)}
@@ -310,6 +312,7 @@ if __name__ == "__main__":
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--balance", action="store_true", help="tiles: equalise the enlarged tile sizes (border tiles own more)")
     a = ap.parse_args()
     if a.mode == "torch":
         a.frames = a.frames or 10
