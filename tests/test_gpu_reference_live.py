@@ -119,3 +119,51 @@ def test_reference_stream_protocol_live_matches_ours():
         torch.backends.cudnn.allow_tf32 = old
         ref_net.reset()
         net.reset()
+
+
+def _make_sequence_folder(d, n, h, w, ext, seed):
+    import cv2
+    import numpy as np
+    os.makedirs(d, exist_ok=True)
+    _, clean = O.make_synthetic_clip(n, h, w, seed=seed)
+    for i in range(n):
+        img = (clean[i].clamp(0, 1) * 255).round().byte().permute(1, 2, 0).numpy()[:, :, ::-1]
+        assert cv2.imwrite(os.path.join(d, f"{i:05d}.{ext}"), np.ascontiguousarray(img))
+
+
+@needs_ref
+def test_run_test_py_runs_unchanged_through_the_plugin():
+    """The reference's whole validation pipeline (run_test.py -> basicsr test_pipeline -> ValFolderDataset ->
+    DenoisingModel.validation: pad, denoise_seq, crop, tensor2img, imwrite, calculate_psnr / psnr_float / ssim)
+    with options/test/bsvd_c64.yml unchanged and ARCH_REGISTRY['BSVD'] resolving to the B200 class.  The yml's
+    dataset folders (Set8, DAVIS) are dangling links in the reference; small synthetic sequences stand in."""
+    import glob
+    import shutil
+    ck = os.path.join(REF, "experiments", "pretrained_ckpt")
+    os.makedirs(ck, exist_ok=True)
+    torch.save({"params": O.make_synthetic_params(0, 0.5)}, os.path.join(ck, "bsvd-64.pth"))
+    shutil.rmtree(os.path.join(REF, "datasets"), ignore_errors=True)
+    shutil.rmtree(os.path.join(REF, "results"), ignore_errors=True)
+    _make_sequence_folder(os.path.join(REF, "datasets", "Set8", "tractor"), 5, 46, 62, "png", 1)     # odd size: pad / crop
+    _make_sequence_folder(os.path.join(REF, "datasets", "Set8", "park"), 4, 48, 64, "png", 2)
+    _make_sequence_folder(os.path.join(REF, "datasets", "DAVIS-2017-test-dev-480p", "JPEGImages", "480p", "aerobatics"),
+                          5, 48, 80, "jpg", 3)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "bsvd_b200.plugin", REF, "run_test.py", "-opt", "options/test/bsvd_c64.yml"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
+    out = r.stdout + "\n" + r.stderr
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "run_test_py_through_plugin.log"), "w") as f:
+        f.write(out)
+    assert r.returncode == 0, out[-4000:]
+    assert stage_reference.verify(REF) > 50                       # run_test.py, the yml, the pipeline: untouched
+    stats = json.loads(re.search(r"bsvd_b200\.plugin: (\{.*\})", out).group(1))
+    # 5 Set8 entries x 2 folders + 5 DAVIS entries x 1 folder = 15 validated sequences, one forward each
+    assert stats["instances"] == 1 and stats["forward_calls"] == 15, stats
+    assert stats["kernel_launches"] == 32 * 15, stats
+    pngs = glob.glob(os.path.join(REF, "results", "bsvd_c64", "visualization", "**", "*.png"), recursive=True)
+    assert len(pngs) == 5 * (5 + 4) + 5 * 5, len(pngs)            # one PNG per validated frame
+    assert "psnr_float" in out and "ssim" in out
+    import cv2
+    img = cv2.imread(sorted(p for p in pngs if "tractor" in p)[0])
+    assert img is not None and img.shape == (46, 62, 3)           # cropped back to the odd source size
