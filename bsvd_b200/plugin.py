@@ -114,9 +114,38 @@ fi
     return w
 
 
-def run_reference_script(path: str, reference_root: str):
+def reseed_after_model_build():
+    """A/B harness only.  The reference seeds the CPU generator once (options.py: set_random_seed), then builds
+    the model (weight init draws from that generator) and only then synthesises the validation noise
+    (ValFolderDataset.__getitem__).  Two model classes that draw a different amount of random numbers in their
+    constructors therefore see DIFFERENT noise.  Re-applying the seed right after build_model makes runs with
+    different classes denoise the same frames; nothing in the reference tree is touched."""
+    import torch
+    models = importlib.import_module("basicsr.models")
+    orig = models.build_model
+
+    def build_model(opt):
+        m = orig(opt)
+        seed = opt.get("manual_seed", 0) or 0
+        import random
+        import numpy as np
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+        return m
+
+    models.build_model = build_model
+    for name in ("basicsr.test", "basicsr.train", "basicsr"):
+        mod = sys.modules.get(name)
+        if mod is not None and getattr(mod, "build_model", None) is orig:
+            mod.build_model = build_model
+
+
+def run_reference_script(path: str, reference_root: str, install_b200: bool = True, reseed: bool = False):
     """`python -m bsvd_b200.plugin <reference_root> profile.py`: run an unmodified reference entry
-    point (profile.py, run_test.py) with the B200 class installed under ARCH_REGISTRY['BSVD']."""
+    point (profile.py, run_test.py) with the B200 class installed under ARCH_REGISTRY['BSVD'].
+    `--reference-only` runs the same script in the same harness with the reference's own class."""
     import os
     import runpy
     sys.path.append(os.path.join(reference_root, "BasicSR"))
@@ -126,13 +155,26 @@ def run_reference_script(path: str, reference_root: str):
     reference_root = os.path.abspath(reference_root)
     stub_optional_dependencies()
     ensure_legacy_nvidia_smi()
-    install()
-    from .arch import BSVD
-    atexit.register(lambda: print("bsvd_b200.plugin: " + json.dumps(BSVD.stats), flush=True))
+    if install_b200:
+        install()
+        from .arch import BSVD
+        atexit.register(lambda: print("bsvd_b200.plugin: " + json.dumps(BSVD.stats), flush=True))
+    else:
+        # same harness (stubs, cwd, argv), the reference's own BSVD class: the A side of an A/B run
+        importlib.import_module("Experimental_root.archs")
+        atexit.register(lambda: print("bsvd_b200.plugin: reference class left in place", flush=True))
+    if reseed:
+        importlib.import_module("basicsr.test")
+        reseed_after_model_build()
     os.chdir(reference_root)
     sys.argv = [os.path.join(reference_root, path)] + sys.argv[3:]
     runpy.run_path(os.path.join(reference_root, path), run_name="__main__")
 
 
 if __name__ == "__main__":
-    run_reference_script(sys.argv[2], sys.argv[1])
+    # python -m bsvd_b200.plugin [--reference-only] [--reseed-after-build] <reference_root> <script> [script args...]
+    flags = set()
+    while len(sys.argv) > 1 and sys.argv[1] in ("--reference-only", "--reseed-after-build"):
+        flags.add(sys.argv.pop(1))
+    run_reference_script(sys.argv[2], sys.argv[1], install_b200="--reference-only" not in flags,
+                         reseed="--reseed-after-build" in flags)

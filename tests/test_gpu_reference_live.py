@@ -167,3 +167,45 @@ def test_run_test_py_runs_unchanged_through_the_plugin():
     import cv2
     img = cv2.imread(sorted(p for p in pngs if "tractor" in p)[0])
     assert img is not None and img.shape == (46, 62, 3)           # cropped back to the odd source size
+    # A/B/C/D on the same pipeline and seeds (the noise comes from the seeded CPU generator, so every run
+    # denoises the same frames):
+    # (`--reseed-after-build`: both classes must see the same noise although their constructors draw a different
+    #  amount of random numbers for the weight init, see plugin.reseed_after_model_build)
+    #   A  ours, yml unchanged (val.fp16: True -> our default fp16 mode)
+    #   B  the reference's own class, yml unchanged (its fp16 autocast)
+    #   C  the reference's own class in true fp32: the reference CLI's own override `--force_yml val:fp16=false`
+    #      plus NVIDIA_TF32_OVERRIDE=0 (PyTorch would otherwise run the "fp32" convs in TF32)
+    #   D  ours in the fp32-grade mode (BSVD_B200_PRECISION=fp32x3) with the same override
+    pat = re.compile(r"# (psnr_float|ssim): ([0-9.]+)")
+
+    def run(tag, extra_args, extra_env, reference_only):
+        shutil.rmtree(os.path.join(REF, "results"), ignore_errors=True)
+        cmd = [sys.executable, "-m", "bsvd_b200.plugin", "--reseed-after-build"] + (["--reference-only"] if reference_only else []) + \
+              [REF, "run_test.py", "-opt", "options/test/bsvd_c64.yml"] + extra_args
+        rr = subprocess.run(cmd, cwd=ROOT, env=dict(env, **extra_env), capture_output=True, text=True, timeout=1200)
+        o = rr.stdout + "\n" + rr.stderr
+        with open(os.path.join(ROOT, "gpurun_out", f"run_test_py_{tag}.log"), "w") as f:
+            f.write(o)
+        assert rr.returncode == 0, o[-4000:]
+        return o, [(k, float(v)) for k, v in pat.findall(o)]
+
+    _, m_a = run("A_ours_fp16", [], {}, False)
+    out_b, m_b = run("B_reference_fp16", [], {}, True)
+    assert "reference class left in place" in out_b
+    fp32 = ["--force_yml", "val:fp16=false"]
+    _, m_c = run("C_reference_fp32", fp32, {"NVIDIA_TF32_OVERRIDE": "0"}, True)
+    _, m_d = run("D_ours_fp32x3", fp32, {"BSVD_B200_PRECISION": "fp32x3"}, False)
+    assert len(m_a) == len(m_b) == len(m_c) == len(m_d) >= 22
+    worst = {"A": 0.0, "B": 0.0, "D": 0.0}
+    for (k, a), (_, b), (_, c), (_, d) in zip(m_a, m_b, m_c, m_d):
+        if k != "psnr_float":
+            assert abs(a - c) <= 2e-3 and abs(d - c) <= 2e-4, (k, a, b, c, d)      # SSIM
+            continue
+        worst["A"] = max(worst["A"], abs(a - c))
+        worst["B"] = max(worst["B"], abs(b - c))
+        worst["D"] = max(worst["D"], abs(d - c))
+    with open(os.path.join(ROOT, "gpurun_out", "run_test_py_abcd.json"), "w") as f:
+        json.dump({"worst_abs_psnr_float_delta_vs_reference_fp32_dB": worst, "metrics_compared": len(m_a)}, f)
+    assert worst["A"] <= 0.01, worst             # our default mode: within 0.01 dB of the reference's fp32 run
+    assert worst["D"] <= 0.001, worst            # our fp32-grade mode: within 0.001 dB
+    assert worst["A"] <= worst["B"] + 1e-3, worst   # and never further from fp32 than the reference's own fp16 run
