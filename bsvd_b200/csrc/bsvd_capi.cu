@@ -741,8 +741,10 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   float* norm = L.first_u8 ? L.first_norm : nullptr;
   const bool bf = (L.p.flags & EPI_BF16) != 0;
+  ConvParams pr = L.p;
+  if (raw) pr.stg_bytes_per_warp = kStageBytesPerWarp;     // RAW instances: one staging tile per epilogue warp
 #define BSVD_FIRST(B, U, R) \
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<B, U, R>, L.first_in, L.first_nmap, L.first_inc, L.map_o, L.p, norm, L.map_raw, L.map_rawnm))
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<B, U, R>, L.first_in, L.first_nmap, L.first_inc, L.map_o, pr, norm, L.map_raw, L.map_rawnm))
   if (raw) { if (bf) BSVD_FIRST(true, false, true); else BSVD_FIRST(false, false, true); }
   else if (L.first_u8) { if (bf) BSVD_FIRST(true, true, false); else BSVD_FIRST(false, true, false); }
   else { if (bf) BSVD_FIRST(true, false, false); else BSVD_FIRST(false, false, false); }

@@ -9,7 +9,8 @@
 //              map) -> 16-bit swizzled rows, fence.proxy.async
 //   warp  8    MMA issuer (8 MMAs per 2-row tile, filter bank resident)
 //   warps 9-16 epilogue (shared with conv_tc.cuh: bias, ReLU6, staged coalesced NHWC stores)
-//   warp  17   RAW instances only: TMA loader of the raw fp32 tiles
+//   RAW instances use another split of the same roles: 4 producer warps, the MMA warp, 16 epilogue warps and a
+//   TMA loader warp for the raw fp32 tiles (see kFirstThreadsRaw)
 // RAW = true (plain fp32 NCHW input, no reflection): the haloed raw tile [4 planes][4 rows][136 px] of
 // every tile is fetched by TMA into a 6-deep shared-memory ring, several tiles ahead (out-of-bounds = the
 // conv's zero padding), and the producers read their 48 values with conflict-free LDS.  With direct global
@@ -21,8 +22,8 @@
 namespace bsvd {
 
 constexpr int kFirstR = 2;
-constexpr int kFirstThreads = 32 * 17;
-constexpr int kFirstProducers = 128;
+constexpr int kFirstThreads = 32 * 17;        // direct-load instances: 8 producer + 1 MMA + 8 epilogue warps
+constexpr int kFirstProducers = 128;          // threads of one producer group
 constexpr int kFirstStages = 4;
 constexpr uint32_t kFirstAStage = kFirstR * kRunPx * 128;   // 32 KB
 constexpr uint32_t kFirstW = 64 * 128;                      // 8 KB
@@ -40,8 +41,15 @@ constexpr int kRawRows = kFirstR + 2;
 constexpr uint32_t kRawPlane = kRawRows * kRawPx * 4;        // 2176 B
 constexpr uint32_t kRawStage = 4 * kRawPlane;                // 8704 B (4 channel planes)
 static_assert(kRawPlane % 128 == 0, "TMA destinations must be 128-byte aligned");
-constexpr size_t kFirstSmemRaw = kFirstSmem + kRawStages * kRawStage;
-constexpr int kFirstThreadsRaw = kFirstThreads + 32;
+// RAW instances: the producers no longer wait on DRAM, so ONE group of 4 warps keeps up; the warps saved go to
+// the epilogue — 16 epilogue warps, one unit each per tile — which is what the kernel was waiting for (the ncu
+// source page showed the producers parked 35 % of all samples behind the eight epilogue warps).
+//   warps 0-3 producers | warp 4 MMA | warps 5-20 epilogue | warp 21 raw-tile loader
+constexpr int kFirstStagesRaw = 3;
+constexpr int kFirstEpiWarpsRaw = 16;
+constexpr size_t kFirstSmemRaw = 1024 + kFirstStagesRaw * kFirstAStage + kFirstW +
+                                 kFirstEpiWarpsRaw * kStageBytesPerWarp + kRawStages * kRawStage;
+constexpr int kFirstThreadsRaw = 32 * (4 + 1 + kFirstEpiWarpsRaw + 1);
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -63,6 +71,13 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   constexpr int NT = 64;
   constexpr int kAccCols = kFirstR * NT;
   constexpr int kTmemCols = 2 * kAccCols;
+  constexpr int kStages = RAW ? kFirstStagesRaw : kFirstStages;       // patch stages
+  constexpr int kProdWarps = RAW ? 4 : 8, kGroups = kProdWarps / 4;    // producer groups of 4 warps
+  constexpr int kMmaWarp = kProdWarps;
+  constexpr int kEpiWarps = RAW ? kFirstEpiWarpsRaw : 8;
+  constexpr int kEpi0 = kMmaWarp + 1;                                  // first epilogue warp
+  constexpr int kLoaderWarp = kEpi0 + kEpiWarps;                       // RAW only
+  constexpr uint32_t kStgPerWarp = RAW ? kStageBytesPerWarp : 2 * kStageBytesPerWarp;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kFirstStages + 5 + 2 * kRawStages];
   __shared__ uint32_t tmem_base_slot;
@@ -70,7 +85,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t w_base = a_base + kFirstStages * kFirstAStage;
+  const uint32_t w_base = a_base + kStages * kFirstAStage;
   const uint32_t stg_base = w_base + kFirstW;
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8u * s; };
@@ -80,17 +95,17 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   const uint32_t w_full = bar0 + 8u * (2 * kFirstStages + 4);
   auto raw_full = [&](int s) { return bar0 + 8u * (2 * kFirstStages + 5 + s); };
   auto raw_empty = [&](int s) { return bar0 + 8u * (2 * kFirstStages + 5 + kRawStages + s); };
-  const uint32_t raw_base = stg_base + 8 * 2 * kStageBytesPerWarp;
+  const uint32_t raw_base = stg_base + kEpiWarps * kStgPerWarp;
   constexpr int kNumThreads = RAW ? kFirstThreadsRaw : kFirstThreads;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFirstStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(a_full(s), kFirstProducers);
       mbar_init(a_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 8);
+      mbar_init(acc_empty(b), kEpiWarps);
     }
     mbar_init(w_full, 1);
     if constexpr (RAW) {
@@ -102,14 +117,14 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     fence_barrier_init();
   }
   // K slots 36..63 of every patch row are zero for the whole kernel: clear the stages once
-  for (uint32_t off = threadIdx.x * 16; off < kFirstStages * kFirstAStage; off += kNumThreads * 16)
+  for (uint32_t off = threadIdx.x * 16; off < kStages * kFirstAStage; off += kNumThreads * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + off), "r"(0) : "memory");
   if constexpr (RAW) {
     // a channel plane no TMA box ever fills (blind 3-channel input) must read as zero, not as garbage
     for (uint32_t off = threadIdx.x * 16; off < kRawStages * kRawStage; off += kNumThreads * 16)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(raw_base + off), "r"(0) : "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -122,7 +137,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
   pdl_launch_dependents();
   pdl_wait();
 
-  if (warp < 8) {
+  if (warp < kProdWarps) {
     // =================================== patch producers ===================================
     // thread = one x position of the 128-px run; it builds the patch rows of both tile rows
     // (they share two of their three input rows).  Group g = warp/4 handles every second tile, so
@@ -132,8 +147,8 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     const int sH = p.src_H ? p.src_H : p.H, sW = p.src_W ? p.src_W : p.W;   // raw image (reflected beyond)
     const long long plane = static_cast<long long>(sH) * sW;
     uint32_t it = grp;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
-      const uint32_t sa = it % kFirstStages, pa = (it / kFirstStages) & 1;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += kGroups * gridDim.x, it += kGroups) {
+      const uint32_t sa = it % kStages, pa = (it / kStages) & 1;
       const TileCoord tc = decode_tile<kFirstR>(p, tile);
       const int x = tc.x0 + i;
       // 4 input rows (y0-1 .. y0+2) x 3 columns x 4 channels.  Row / column offsets (with the
@@ -242,7 +257,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
       mbar_arrive_release(a_full(sa));
     }
-  } else if (RAW && warp == 17) {
+  } else if (RAW && warp == kLoaderWarp) {
     // ===================================== raw-tile loader =====================================
     if (lane == 0) {
       const int nm_planes = (nmap != nullptr) ? 1 : 0;
@@ -258,7 +273,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         if (nm_planes) tma_load_3d(dst + in_c * kRawPlane, &map_rawnm, raw_full(rs), tc.x0 - kRawLead, tc.y0 - 1, tc.t);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ====================================== MMA issuer ======================================
     // 32 output channels (c32 configurations): N = 32, the accumulator keeps its 64-column row pitch
     const uint32_t idesc = make_idesc(p.out_C == 32 ? 32 : NT, BF16 ? 1 : 0);
@@ -291,17 +306,52 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
         umma_commit(acc_full(buf));
       }
       __syncwarp();
-      if (++sa == kFirstStages) { sa = 0; pa ^= 1; }
+      if (++sa == kStages) { sa = 0; pa ^= 1; }
     }
   } else {
     // ======================================= epilogue =======================================
-    const int ew = warp - 9;                   // 0..7
-    const int quad = warp & 3;
-    const int half = ew >> 2;
-    const uint32_t stg = stg_base + ew * 2 * kStageBytesPerWarp;
+    const int ew = warp - kEpi0;               // 0 .. kEpiWarps-1
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int G = NT / 32;
+    constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
+    // which of the kEpiWarps / 4 warps of this quadrant: they split the R * G units of a tile
+    int sub = 0;
+    for (int w = kEpi0; w < warp; ++w) sub += ((w & 3) == quad) ? 1 : 0;
     uint32_t it = 0;
+    if constexpr (RAW) {
+      // 16 epilogue warps: one unit (row u / G, column group u % G) per warp and tile, one staging tile per warp
+      const uint32_t stg = stg_base + ew * kStgPerWarp;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile<kFirstR>(p, tile);
+        EpiLane el = epi_lane<EPI_RELU6 | EPI_RELU>(p, lane);
+        el.nvalid = min(32, p.W - (tc.x0 + quad * 32));
+        const uint32_t buf = it & 1, acc_phase = (it >> 1) & 1;
+        const int units = (p.out_C == 32) ? kFirstR : kFirstR * G;      // 32 stored channels: one unit per row
+        const int row = (p.out_C == 32) ? sub : sub / G, grp32 = (p.out_C == 32) ? 0 : sub % G;
+        mbar_wait(acc_full(buf), acc_phase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
+        uint32_t va[32];
+        if (sub < units) {
+          tmem_ld32(tacc + row * NT + grp32 * 32, va);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(buf));
+        if (sub < units) {
+          const uint4 nosk[4] = {};
+          const float norin[3] = {};
+          float bv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[grp32 * 32 + i];
+          epilogue_unit<BF16, kEpiMask>(p, tc, el, tc.y0 + row, grp32 * 32, va, nosk, bv, stg, quad, lane, norin, false, &map_o);
+        }
+      }
+    } else {
+    const int half = sub;
+    const uint32_t stg = stg_base + ew * kStgPerWarp;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile<kFirstR>(p, tile);
       EpiLane el = epi_lane<EPI_RELU6 | EPI_RELU>(p, lane);
@@ -310,7 +360,6 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       mbar_wait(acc_full(buf), acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + lane_base + buf * kAccCols;
-      constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
       const uint4 nosk[4] = {};
       const float norin[3] = {};
       if (p.out_C == 32) {
@@ -345,12 +394,13 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
       for (int i = 0; i < 32; ++i) bv[i] = p.bias_c[((u0 + 1) % G) * 32 + i];
       epilogue_unit<BF16, kEpiMask>(p, tc, el, tc.y0 + (u0 + 1) / G, ((u0 + 1) % G) * 32, vb, nosk, bv, stg + kStageBytesPerWarp, quad, lane, norin, false, &map_o);
     }
+    }
     if (lane == 0) bulk_wait_group_all();      // staging must outlive the last TMA reads
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
