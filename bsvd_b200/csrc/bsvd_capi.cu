@@ -462,6 +462,14 @@ struct StageIO {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// reciprocals for decode_tile (ConvParams::fast_div): exact while dividend * divisor < 2^32
+static void set_tile_div(ConvParams& p) {
+  auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+  const uint64_t max_n = (uint64_t)std::max(p.positions, p.total_tiles) + 2;
+  const uint64_t max_d = (uint64_t)std::max(std::max(p.n_tiles, p.xblocks), std::max(p.yblocks, 1));
+  p.fast_div = (max_n * max_d < (1ull << 32)) ? 1 : 0;
+  p.div_nt = magic(p.n_tiles); p.div_xb = magic(p.xblocks); p.div_yb = magic(p.yblocks);
+}
 static size_t staging_bytes(int ew) { return (size_t)ew * kStageBytesPerWarp; }   // epilogue staging
 
 // conv3x3_tc_kernel instances live in their own translation units (conv_inst.cu, compiled once per
@@ -559,6 +567,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.yblocks = (Ho + kFirstR - 1) / kFirstR;
     p.positions = p.T * p.yblocks * p.xblocks;
     p.total_tiles = p.positions;
+    set_tile_div(p);
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = (s.relu ? EPI_RELU : EPI_RELU6) | (bf16 ? EPI_BF16 : 0);
     const int oc = s.store_c ? s.store_c : s.cout;     // 32: only the first unit of every row is stored
@@ -582,6 +591,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.n_tiles = 1;
     p.positions = p.T * p.yblocks * p.xblocks;
     p.total_tiles = p.positions;
+    set_tile_div(p);
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = EPI_FINAL | (bf16 ? EPI_BF16 : 0);
     p.out = io.out; p.out_C = 3; p.out_H = Ho; p.out_W = Wo;
@@ -597,6 +607,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   }
   p.positions = p.T * p.yblocks * p.xblocks;
   p.total_tiles = (cta2 ? (p.positions + 1) / 2 : p.positions) * p.n_tiles;
+  set_tile_div(p);
   p.mode = (s.stride == 2) ? 1 : 0;
   p.cin_total = s.split ? 2 * s.cin : s.cin;          // channels per pixel as stored (stride-2 column parity offset)
   p.phys_chunks = s.split ? 2 * s.cin / kChunk : 0;
@@ -727,6 +738,8 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmem));
     CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
     CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
+    CUDA_TRY(cudaFuncSetAttribute(first_conv_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFirstSmemRaw));
     attr_done[dev & 63] = true;
   }
   if (!L.first_in) return fail("first stage launched without an input pointer");
@@ -743,9 +756,11 @@ static int launch_first(const StageLaunch& L, cudaStream_t st) {
   const bool bf = (L.p.flags & EPI_BF16) != 0;
   ConvParams pr = L.p;
   if (raw) pr.stg_bytes_per_warp = kStageBytesPerWarp;     // RAW instances: one staging tile per epilogue warp
-#define BSVD_FIRST(B, U, R) \
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<B, U, R>, L.first_in, L.first_nmap, L.first_inc, L.map_o, pr, norm, L.map_raw, L.map_rawnm))
-  if (raw) { if (bf) BSVD_FIRST(true, false, true); else BSVD_FIRST(false, false, true); }
+  const bool act6 = (L.p.flags & EPI_RELU6) && !(L.p.flags & EPI_RELU);
+#define BSVD_FIRST(B, U, R, ...) \
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, first_conv_kernel<B, U, R, ##__VA_ARGS__>, L.first_in, L.first_nmap, L.first_inc, L.map_o, pr, norm, L.map_raw, L.map_rawnm))
+  if (raw && act6) { if (bf) BSVD_FIRST(true, false, true, true); else BSVD_FIRST(false, false, true, true); }
+  else if (raw) { if (bf) BSVD_FIRST(true, false, true); else BSVD_FIRST(false, false, true); }
   else if (L.first_u8) { if (bf) BSVD_FIRST(true, true, false); else BSVD_FIRST(false, true, false); }
   else { if (bf) BSVD_FIRST(true, false, false); else BSVD_FIRST(false, false, false); }
 #undef BSVD_FIRST

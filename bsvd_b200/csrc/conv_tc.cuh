@@ -110,6 +110,12 @@ struct ConvParams {
   int xblocks, yblocks; // ceil(W/128), ceil(H/R)
   int total_tiles;      // 1-CTA: positions*n_tiles; CTA pair: ceil(positions/2)*n_tiles
   int positions;        // T*yblocks*xblocks pixel tiles
+  // decode_tile runs once per tile in every warp of every role: its three divisions by run-time values were
+  // ~80 of the ~330 instructions an epilogue warp issues per unit (ncu, first conv).  The host supplies
+  // ceil(2^32 / d) for d = n_tiles, xblocks, yblocks (0 for d == 1) when every dividend n satisfies
+  // n * d < 2^32, which makes umulhi(n, magic) == n / d exact; otherwise fast_div = 0 and the kernels divide.
+  int fast_div;
+  uint32_t div_nt, div_xb, div_yb;
   int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2, generic pipeline only),
                         // 2 = halo with the vertical taps stacked in N (64->64 stages, see below),
                         // 4 = stride 2 with one box per input sub-plane (see s2_slab)
@@ -460,17 +466,22 @@ struct TileCoord {
 // CTA2: `tile` indexes (pair of neighbouring pixel tiles, n tile); CTA `rank` takes position
 // 2*pair+rank.  A position past the end (odd count) yields t == T: every TMA box is then fully
 // out of bounds (zero fill) and the epilogue stores nothing.
+// n / d for a divisor whose reciprocal the host prepared (see ConvParams::fast_div)
+__device__ __forceinline__ int tile_div(const ConvParams& p, int n, int d, uint32_t magic) {
+  if (p.fast_div) return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n;
+  return n / d;
+}
 template <int R>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int cta2 = 0,
                                                  int rank = 0) {
   TileCoord c;
-  c.nt = tile % p.n_tiles;
-  int s = tile / p.n_tiles;
+  int s = tile_div(p, tile, p.n_tiles, p.div_nt);
+  c.nt = tile - s * p.n_tiles;
   if (cta2) s = 2 * s + rank;
-  int xb = s % p.xblocks;
-  s /= p.xblocks;
-  int yb = s % p.yblocks;
-  c.t = s / p.yblocks;
+  const int q = tile_div(p, s, p.xblocks, p.div_xb);
+  const int xb = s - q * p.xblocks;
+  c.t = tile_div(p, q, p.yblocks, p.div_yb);
+  const int yb = q - c.t * p.yblocks;
   c.y0 = yb * R;
   c.x0 = xb * kRunPx;
   return c;
@@ -725,6 +736,10 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
   const int flags = p.flags & MASK;
   constexpr bool kSplit = (MASK & EPI_SPLIT) != 0;
   static_assert(!(kSplit && BF16), "the fp32-grade split uses fp16 pieces");
+  // Instances compiled with EPI_RELU6 but without EPI_RELU serve only stages that DO apply ReLU6 (the
+  // dispatch in stage_launch.cuh guarantees it): the clamp is unconditional, and the fp16 range guard and the
+  // plain-ReLU path — predicated off but still issued in the general instances — are not compiled at all.
+  constexpr bool kOnly6 = (MASK & EPI_RELU6) != 0 && (MASK & EPI_RELU) == 0 && !kSplit;
 
   // ------------------------------ phase 0 ------------------------------
   // hand the coalesced skip operand over to the pixel-owning lanes through the staging tile
@@ -764,7 +779,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
     }
     // range guard: running maximum of what this lane stores (|x|, or x under ReLU, which clamps the
     // negative side); ReLU6 stages are bounded and skip it
-    const bool chk_range = !BF16 && !(flags & EPI_RELU6) && p.overflow != nullptr;
+    const bool chk_range = !BF16 && !kOnly6 && !(flags & EPI_RELU6) && p.overflow != nullptr;
     const bool chk_signed = (flags & EPI_RELU) != 0;
     float vmax = 0.f;
 #pragma unroll
@@ -841,7 +856,7 @@ __device__ __forceinline__ void epilogue_unit(const P& p, const TileCoord& tc, c
         }
       }
       if constexpr (!kSplit) {
-        if (flags & EPI_RELU6) {
+        if (kOnly6 || (flags & EPI_RELU6)) {
           o[j].x = relu6_packed<BF16>(o[j].x); o[j].y = relu6_packed<BF16>(o[j].y);
           o[j].z = relu6_packed<BF16>(o[j].z); o[j].w = relu6_packed<BF16>(o[j].w);
         } else if (flags & EPI_RELU) {

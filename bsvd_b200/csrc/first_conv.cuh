@@ -61,7 +61,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // B,G,R as cv2 delivers them): normalised with /255 on the fly (img2tensor,
 // BasicSR/basicsr/utils/img_util.py), and the normalised RGB planes of every pixel are also written
 // to `norm_out` (fp32 [T][3][H][W]) for the temp1 residual, which needs the raw input again.
-template <bool BF16, bool U8 = false, bool RAW = false>
+// ACT6 (RAW instances): the stage applies ReLU6 (act 'relu6', the BSVD-64 yml) — the epilogue is compiled without
+// the plain-ReLU path and the fp16 range guard (epilogue_unit, kOnly6).  This kernel is bound by the instructions
+// its epilogue warps issue (ncu: 83 % of all warp instructions, issue slots 55 % busy).
+template <bool BF16, bool U8 = false, bool RAW = false, bool ACT6 = false>
 __global__ void __launch_bounds__(RAW ? kFirstThreadsRaw : kFirstThreads, 1)
 first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, int in_c,
                   const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p,
@@ -314,7 +317,7 @@ first_conv_kernel(const float* __restrict__ in, const float* __restrict__ nmap, 
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     constexpr int G = NT / 32;
-    constexpr int kEpiMask = EPI_RELU6 | EPI_RELU | EPI_TMA_OUT;
+    constexpr int kEpiMask = (ACT6 ? EPI_RELU6 : (EPI_RELU6 | EPI_RELU)) | EPI_TMA_OUT;
     // which of the kEpiWarps / 4 warps of this quadrant: they split the R * G units of a tile
     int sub = 0;
     for (int w = kEpi0; w < warp; ++w) sub += ((w & 3) == quad) ? 1 : 0;

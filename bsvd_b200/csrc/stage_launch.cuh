@@ -117,6 +117,11 @@ constexpr int kMaskUpShift = EPI_PIXSHUF | EPI_SHIFT;   // upc2.convblock.0 with
 constexpr int kMaskUpSkipShift = EPI_PIXSHUF | EPI_SKIP | EPI_SHIFT;   // upc2.convblock.0: skip added in the epilogue
 constexpr int kMaskUpSkip = EPI_PIXSHUF | EPI_SKIP;                    // c32 upc1.convblock.0 (N tile 128)
 constexpr int kMaskAll = kMaskAct | EPI_SHIFT | EPI_PIXSHUF | EPI_SKIP | EPI_RESID_IN;
+// ReLU6-only sets (the BSVD-64 yml: act 'relu6'): the clamp is unconditional, no fp16 range guard, no plain-ReLU
+// path (see epilogue_unit, kOnly6); and temp1's last conv, which has no activation at all
+constexpr int kMaskPlain6 = EPI_RELU6;
+constexpr int kMaskShift6 = EPI_RELU6 | EPI_SHIFT;
+constexpr int kMaskResidOnly = EPI_RESID_IN;
 template <int NTILE, int R, bool BF16>
 static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
   if (L.split) {
@@ -141,6 +146,16 @@ static int launch_dtype(const StageLaunch& L, cudaStream_t st) {
   if (!L.cta2) return launch_inst<NTILE, R, BF16, false, kMaskAll, 8>(L, st);
   const int f = L.p.flags & kMaskAll;
   {
+    if constexpr (!(NTILE == 256 && R == 2)) {
+      const bool only6 = (f & EPI_RELU6) && !(f & EPI_RELU);
+      if (L.p.tma_out) {
+        if (only6 && (f & ~kMaskPlain6) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain6 | EPI_TMA_OUT, 8>(L, st);
+        if constexpr (NTILE == 64)
+          if (f == kMaskResidOnly) return launch_inst<NTILE, R, BF16, true, kMaskResidOnly | EPI_TMA_OUT, 8>(L, st);
+      } else if (only6 && (f & ~kMaskShift6) == 0) {
+        return launch_inst<NTILE, R, BF16, true, kMaskShift6, 8>(L, st);
+      }
+    }
     if (L.p.tma_out) {     // no temporal shift on the output: units leave through TMA stores
       if ((f & ~kMaskPlain) == 0) return launch_inst<NTILE, R, BF16, true, kMaskPlain | EPI_TMA_OUT, 8>(L, st);
       if ((f & ~kMaskResid) == 0) return launch_inst<NTILE, R, BF16, true, kMaskResid | EPI_TMA_OUT, 8>(L, st);
