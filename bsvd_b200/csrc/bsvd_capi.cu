@@ -513,6 +513,8 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   L->cta2 = cta2;
   // 8 epilogue warps: 16 were measured (kernel template parameter EW) and bring nothing — the
   // gap between a full stage and its epilogue-less run is shared-memory/L2 contention, not latency
+  // (re-measured in round 2 on upc1.convblock.0, the stage with the longest epilogue — 8 units of ~175
+  // instructions per warp and tile: 0.61 -> 0.63-0.67 ms with 16 warps and one staging tile each)
   L->ew = 8;
   // PixelShuffle + skip stages on the CTA-pair <256,1> kernel: the skip tensor is accumulated by an
   // identity MMA (TMA-loaded like an extra K chunk); without a temporal shift on the output the
