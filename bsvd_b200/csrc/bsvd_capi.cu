@@ -462,13 +462,19 @@ struct StageIO {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// reciprocals for decode_tile (ConvParams::fast_div): exact while dividend * divisor < 2^32
-static void set_tile_div(ConvParams& p) {
+// reciprocals for decode_tile (ConvParams::div_nt ...): umulhi(n, ceil(2^32 / d)) == n / d while n * d < 2^32
+static int set_tile_div(ConvParams& p) {
   auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
-  const uint64_t max_n = (uint64_t)std::max(p.positions, p.total_tiles) + 2;
-  const uint64_t max_d = (uint64_t)std::max(std::max(p.n_tiles, p.xblocks), std::max(p.yblocks, 1));
-  p.fast_div = (max_n * max_d < (1ull << 32)) ? 1 : 0;
+  // the three dividends of decode_tile: tile index, pixel-tile position (one past the end for the padding tile
+  // of an odd CTA pair), position / xblocks
+  const uint64_t n1 = (uint64_t)p.total_tiles + 1, n2 = (uint64_t)p.positions + 2,
+                 n3 = n2 / (uint64_t)std::max(p.xblocks, 1) + 1;
+  const uint64_t lim = 1ull << 32;
+  if (n1 * (uint64_t)p.n_tiles >= lim || n2 * (uint64_t)p.xblocks >= lim || n3 * (uint64_t)p.yblocks >= lim)
+    return fail("too many tiles for one launch (%d frames of %d x %d tile rows / columns): split the clip", p.T,
+                p.yblocks, p.xblocks);
   p.div_nt = magic(p.n_tiles); p.div_xb = magic(p.xblocks); p.div_yb = magic(p.yblocks);
+  return 0;
 }
 static size_t staging_bytes(int ew) { return (size_t)ew * kStageBytesPerWarp; }   // epilogue staging
 
@@ -569,7 +575,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.yblocks = (Ho + kFirstR - 1) / kFirstR;
     p.positions = p.T * p.yblocks * p.xblocks;
     p.total_tiles = p.positions;
-    set_tile_div(p);
+    if (set_tile_div(p)) return 1;
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = (s.relu ? EPI_RELU : EPI_RELU6) | (bf16 ? EPI_BF16 : 0);
     const int oc = s.store_c ? s.store_c : s.cout;     // 32: only the first unit of every row is stored
@@ -593,7 +599,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
     p.n_tiles = 1;
     p.positions = p.T * p.yblocks * p.xblocks;
     p.total_tiles = p.positions;
-    set_tile_div(p);
+    if (set_tile_div(p)) return 1;
     p.wpack = sd.wpack; p.bias = sd.bias;
     p.flags = EPI_FINAL | (bf16 ? EPI_BF16 : 0);
     p.out = io.out; p.out_C = 3; p.out_H = Ho; p.out_W = Wo;
@@ -609,7 +615,7 @@ static int plan_stage(const StageDev& sd, const StageIO& io, int bf16, int desc_
   }
   p.positions = p.T * p.yblocks * p.xblocks;
   p.total_tiles = (cta2 ? (p.positions + 1) / 2 : p.positions) * p.n_tiles;
-  set_tile_div(p);
+  if (set_tile_div(p)) return 1;
   p.mode = (s.stride == 2) ? 1 : 0;
   p.cin_total = s.split ? 2 * s.cin : s.cin;          // channels per pixel as stored (stride-2 column parity offset)
   p.phys_chunks = s.split ? 2 * s.cin / kChunk : 0;

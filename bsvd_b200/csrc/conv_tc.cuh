@@ -112,9 +112,12 @@ struct ConvParams {
   int positions;        // T*yblocks*xblocks pixel tiles
   // decode_tile runs once per tile in every warp of every role: its three divisions by run-time values were
   // ~80 of the ~330 instructions an epilogue warp issues per unit (ncu, first conv).  The host supplies
-  // ceil(2^32 / d) for d = n_tiles, xblocks, yblocks (0 for d == 1) when every dividend n satisfies
-  // n * d < 2^32, which makes umulhi(n, magic) == n / d exact; otherwise fast_div = 0 and the kernels divide.
-  int fast_div;
+  // ceil(2^32 / d) for d = n_tiles, xblocks, yblocks (0 for d == 1): umulhi(n, magic) == n / d is exact while
+  // n * d < 2^32, which plan_stage checks for each of the three dividends (it fails otherwise: such a launch
+  // would need a workspace far beyond the 180 GB of the device).  The instances with the skip add in their
+  // epilogue (EPI_SKIP) keep the plain divisions: they sit on the 168-register ceiling of a 320-thread CTA, and
+  // with the shorter coordinate code ptxas schedules their skip loads earlier and spills (measured: the c32
+  // upc1.convblock.0 stage 0.22 -> 0.45 ms); their epilogues are not instruction-bound anyway.
   uint32_t div_nt, div_xb, div_yb;
   int mode;             // 0 = halo (stride 1), 1 = per-tap boxes (stride 2, generic pipeline only),
                         // 2 = halo with the vertical taps stacked in N (64->64 stages, see below),
@@ -466,24 +469,35 @@ struct TileCoord {
 // CTA2: `tile` indexes (pair of neighbouring pixel tiles, n tile); CTA `rank` takes position
 // 2*pair+rank.  A position past the end (odd count) yields t == T: every TMA box is then fully
 // out of bounds (zero fill) and the epilogue stores nothing.
-// n / d for a divisor whose reciprocal the host prepared (see ConvParams::fast_div)
-__device__ __forceinline__ int tile_div(const ConvParams& p, int n, int d, uint32_t magic) {
-  if (p.fast_div) return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n;
-  return n / d;
+// n / d for a divisor whose reciprocal the host prepared (see ConvParams::div_nt)
+__device__ __forceinline__ int tile_div(int n, uint32_t magic) {
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n;
 }
-template <int R>
+template <int R, bool FAST = true>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int cta2 = 0,
                                                  int rank = 0) {
   TileCoord c;
-  int s = tile_div(p, tile, p.n_tiles, p.div_nt);
-  c.nt = tile - s * p.n_tiles;
-  if (cta2) s = 2 * s + rank;
-  const int q = tile_div(p, s, p.xblocks, p.div_xb);
-  const int xb = s - q * p.xblocks;
-  c.t = tile_div(p, q, p.yblocks, p.div_yb);
-  const int yb = q - c.t * p.yblocks;
-  c.y0 = yb * R;
-  c.x0 = xb * kRunPx;
+  if constexpr (FAST) {
+    int s = tile_div(tile, p.div_nt);
+    c.nt = tile - s * p.n_tiles;
+    if (cta2) s = 2 * s + rank;
+    const int q = tile_div(s, p.div_xb);
+    const int xb = s - q * p.xblocks;
+    c.t = tile_div(q, p.div_yb);
+    const int yb = q - c.t * p.yblocks;
+    c.y0 = yb * R;
+    c.x0 = xb * kRunPx;
+  } else {
+    c.nt = tile % p.n_tiles;
+    int s = tile / p.n_tiles;
+    if (cta2) s = 2 * s + rank;
+    int xb = s % p.xblocks;
+    s /= p.xblocks;
+    int yb = s % p.yblocks;
+    c.t = s / p.yblocks;
+    c.y0 = yb * R;
+    c.x0 = xb * kRunPx;
+  }
   return c;
 }
 
@@ -894,6 +908,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o,
                   const __grid_constant__ ConvParams p) {
   static_assert(NTILE == 64 || NTILE == 128 || NTILE == 256, "unsupported NTILE");
+  constexpr bool kFastDiv = (MASK & EPI_SKIP) == 0;   // see ConvParams::div_nt
   constexpr int kAccCols = R * NTILE;                 // TMEM columns of one accumulator set
   // two accumulator sets (epilogue of tile i overlaps the MMAs of tile i+1) when they fit in the
   // 512 TMEM columns, otherwise one set (bigger tile: every filter slab is reused for R rows)
@@ -1015,7 +1030,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
       bool first = true;
       for (int tile = tile0; tile < pp.total_tiles; tile += tstep) {
-        const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
+        const TileCoord tc = decode_tile<R, kFastDiv>(p, tile, CTA2, rank);
         int nskip = 0;
         if constexpr ((PIPE == 4 || PIPE == 5) && CTA2) {
           // stride 2, sub-plane boxes: the A boxes and filter slabs of a chunk, issued in consumption order
@@ -1336,7 +1351,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         constexpr int G = NTILE / 32;
         const int u0 = (ew >> 2) * ((R * G) / (EW / 4));
         if ((e.flags & EPI_RESID_IN) && tile_idx < p.total_tiles) {
-          const TileCoord tn = decode_tile<R>(p, tile_idx, CTA2, rank);
+          const TileCoord tn = decode_tile<R, kFastDiv>(p, tile_idx, CTA2, rank);
           const int y = tn.y0 + u0 / G, x = tn.x0 + quad * 32 + lane;
           if (tn.nt * NTILE + (u0 % G) * 32 == 0 && tn.t < e.T && y < e.H && x < e.W) {
             const long long plane = static_cast<long long>(e.src_H) * e.src_W;
@@ -1351,7 +1366,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     };
     load_rin(tile0);
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++it) {
-      const TileCoord tc = decode_tile<R>(p, tile, CTA2, rank);
+      const TileCoord tc = decode_tile<R, kFastDiv>(p, tile, CTA2, rank);
       const uint32_t buf = (kNumAcc == 2) ? (it & 1) : 0u;
       const uint32_t acc_phase = (kNumAcc == 2) ? ((it >> 1) & 1) : (it & 1);
       constexpr int G = NTILE / 32;            // 32-column groups per row

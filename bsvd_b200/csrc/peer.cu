@@ -37,9 +37,13 @@ static StreamWaitValue32Fn get_wait_fn() {
   return fn;
 }
 
-constexpr int kSeqLen = 1 << 20;     // signal values 0 .. 2^20-1 (4 MB pool: seq[i] = i)
-static __global__ void fill_seq_kernel(uint32_t* seq, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) seq[i] = (uint32_t)i;
+// A signal is a 4-byte copy out of a device pool of values: seq[i] = seq_base + i (4 MB).  The pool covers a
+// window of 2^20 consecutive values; a value outside it (once per ~10^6 steps of a long-running service) drains
+// the device and rewrites the pool around the new value, so step counters are good for the full 32 bits.
+constexpr int kSeqLen = 1 << 20;
+constexpr unsigned kSeqSlack = 4096;   // values a little below the newest one stay in the window (late releases)
+static __global__ void fill_seq_kernel(uint32_t* seq, int n, uint32_t base) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) seq[i] = base + (uint32_t)i;
 }
 
 }  // namespace bsvd
@@ -53,7 +57,8 @@ struct bsvd_peer_group {
   int nflags = 0;
   uint8_t* local = nullptr;                 // base of the local allocation (flags first)
   std::vector<uint8_t*> base;               // base[r]: rank r's allocation as mapped here (base[rank] == local)
-  uint32_t* seq = nullptr;                  // device pool of signal values
+  uint32_t* seq = nullptr;                  // device pool of signal values seq_base .. seq_base + kSeqLen - 1
+  uint32_t seq_base = 0;
   bool opened = false;
 };
 
@@ -71,11 +76,17 @@ int bsvd_peer_create(int rank, int world, size_t bytes, int nflags, bsvd_peer_gr
       cudaMalloc((void**)&g->seq, sizeof(uint32_t) * kSeqLen) != cudaSuccess) {
     cudaGetLastError();
     if (g->local) cudaFree(g->local);
+    if (g->seq) cudaFree(g->seq);
     delete g;
     return fail("cudaMalloc of the symmetric peer buffer (%zu bytes) failed", bytes);
   }
-  fill_seq_kernel<<<64, 256>>>(g->seq, kSeqLen);
-  if (cudaDeviceSynchronize() != cudaSuccess) { delete g; return fail("peer group initialisation failed"); }
+  fill_seq_kernel<<<64, 256>>>(g->seq, kSeqLen, 0u);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(g->local); cudaFree(g->seq);
+    delete g;
+    return fail("peer group initialisation failed");
+  }
   g->base.assign(world, nullptr);
   g->base[rank] = g->local;
   if (world == 1) g->opened = true;
@@ -164,9 +175,15 @@ int bsvd_peer_signal(bsvd_peer_group* g, int dst_rank, int flag, unsigned value,
   if (!g) return fail("null argument");
   if (!g->opened) return fail("peer group is not opened yet (bsvd_peer_open)");
   if (dst_rank < 0 || dst_rank >= g->world || flag < 0 || flag >= g->nflags) return fail("bad flag %d on rank %d", flag, dst_rank);
-  if (value >= (unsigned)kSeqLen) return fail("signal value %u exceeds the pool (%d)", value, kSeqLen);
+  if (value < g->seq_base || value - g->seq_base >= (unsigned)kSeqLen) {
+    // every pending signal copy (on any stream) still reads the pool: drain the device before rewriting it
+    CUDA_TRY(cudaDeviceSynchronize());
+    g->seq_base = value > kSeqSlack ? value - kSeqSlack : 0u;
+    fill_seq_kernel<<<64, 256>>>(g->seq, kSeqLen, g->seq_base);
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
   // a 4-byte copy behind the data copies of the same stream: ordered after them, still no SM involved
-  CUDA_TRY(cudaMemcpyAsync(g->base[dst_rank] + (size_t)flag * 4, g->seq + value, 4, cudaMemcpyDeviceToDevice,
+  CUDA_TRY(cudaMemcpyAsync(g->base[dst_rank] + (size_t)flag * 4, g->seq + (value - g->seq_base), 4, cudaMemcpyDeviceToDevice,
                            reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }

@@ -170,3 +170,27 @@ def test_tsn_twin_uses_the_reference_tsn_parameter_names():
     net.train()
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 4, 4, 8, 8))            # no backward pass: refuses under autograd
+
+
+def test_production_kernel_instances_do_not_spill():
+    """Register budget of the built library (cuobjdump -res-usage): a 320-thread CTA leaves 168 registers per
+    thread, the skip-in-the-epilogue instances sit right under that ceiling, and a spill inside their epilogue
+    loop doubled a stage's time once (c32 upc1.convblock.0, 0.22 -> 0.45 ms).  Only the general debug instance
+    (all epilogue features compiled in, mask 543) may use local memory; the first conv at most 16 bytes."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", capi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    funcs = re.findall(r"Function (\S+?):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    conv = [(f, int(r), int(s)) for f, r, s in funcs if "conv3x3_tc_kernel" in f]
+    first = [(f, int(r), int(s)) for f, r, s in funcs if "first_conv_kernel" in f]
+    final = [(f, int(r), int(s)) for f, r, s in funcs if "final_conv_kernel" in f]
+    assert len(conv) >= 100 and len(first) >= 6 and len(final) >= 4, (len(conv), len(first), len(final))
+    general = "ELi%dE" % 543          # kMaskAll: RELU6 | RELU | SHIFT | PIXSHUF | SKIP | RESID_IN
+    bad = [(f, r, s) for f, r, s in conv if s > 0 and general not in f]
+    assert not bad, bad
+    assert all(r <= 168 for _, r, _ in conv)
+    assert all(s <= 16 for _, _, s in first), first
+    assert all(s == 0 for _, _, s in final), final
